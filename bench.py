@@ -1,0 +1,416 @@
+#!/usr/bin/env python
+"""bench.py -- likelihood evaluations per second of the batched TTV engine on B200.
+
+    python bench.py --gpus N --steps K --warmup W [--workload c4|c2|c5|c3] [--impl reference]
+
+A "step" is one pass of the hot path (cube vector -> ephemerides -> chi2 -> logL) over one
+batch of synthetic walkers. Default workload = BASELINE.json configs[3] (C4): synthetic
+three-planet near-resonant system, 1500-day baseline, dt = 0.1 d, 10^5 walkers per GPU --
+the "3-planet config" the north-star target is quoted on. Weak scaling: every rank
+evaluates its own 10^5 walkers; with N > 1 the per-step all-gather of log-likelihoods (the
+sampler's exchange step) is inside the timed region.
+
+Prints ONE JSON line (rank 0). `--impl reference` times the CPU implementation of the same
+path (the oracle port of the TTVFast path, all host cores) on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SEED = 20240607
+# Examples/inputs/trues:13-23 (3-planet true solution; nauyaca order per planet:
+# mass[Mearth] period ecc inclination argument mean_anomaly ascending_node)
+TRUES_3PL = [0.07652, 10.4707, 0.0406, 89.809, 292.62, 246.14, 88.3,
+             1.98033, 14.10509, 0.0244, 89.909, 239.76, 191.31, 88.46,
+             0.6705, 23.57467, 0.0306, 90.336, 82.64, 149.24, 88.51]
+# Documentation/inputs/true_solution (2-planet system)
+TRUES_2PL = [5.66468, 5.35468, 0.1237, 90.7169039033241, 296.22, 16.39, 88.36,
+             26.85598, 11.83319, 0.0727, 90.05186862225226, 187.26, 86.62, 88.95]
+
+# Algorithmic FLOP model of SURVEY.md 8(d) (+,-,*,/,sqrt = 1, FMA = 2)
+F_KEP, F_CHK = 200.0, 6.0
+
+
+def flops_per_eval(npla, nsteps, nconj):
+    f_kick = 25.0 * npla * (npla + 1) / 2.0 + 40.0 * npla
+    f_tr = 2.0 * npla * F_KEP + 2.0 * 4.0 * (F_KEP + 20.0)
+    return nsteps * (npla * F_KEP + f_kick + npla * F_CHK) + nconj * f_tr
+
+
+def load_systems():
+    with open(os.path.join(ROOT, "tests", "golden", "systems.json")) as fh:
+        return json.load(fh)
+
+
+def cube_of(spec, flat):
+    """Hypercube coordinates of a full physical vector (inverse of utils.py:403-438 for the
+    free parameters; constants are dropped)."""
+    flat = np.asarray(flat, dtype=np.float64)
+    const = {int(k) for k in spec["constant_params"]}
+    vals = []
+    for k in range(7 * spec["npla"]):
+        if k in const:
+            continue
+        c = k % 7
+        p = k // 7
+        if c == 4:
+            v = flat[7 * p + 4] + flat[7 * p + 5]
+        elif c == 5:
+            v = flat[7 * p + 4] - flat[7 * p + 5]
+        else:
+            v = flat[k]
+        vals.append(v)
+    bi, bf = np.array(spec["bi"]), np.array(spec["bf"])
+    return (np.array(vals) - bi) / (bf - bi)
+
+
+def make_workload(name, engine_factory):
+    """Returns (spec, X[B, ndim], description). The observed table of the synthetic 1500-d
+    system is the engine's own ephemeris of the true solution (computed once, untimed)."""
+    systems = load_systems()
+    rng = np.random.default_rng(SEED)
+    if name == "c2":
+        spec = dict(systems["doc2"])
+        X = rng.random((10_000, spec["ndim"]))
+        return spec, X, "C2: Documentation 2-planet system (221 d, dt 0.18, 1228 steps, 60 obs), 10^4 U(0,1) DE members"
+    if name == "c3":
+        spec = dict(systems["doc2"])
+        c = cube_of(spec, TRUES_2PL)
+        X = np.clip(c[None, :] + 0.01 * rng.standard_normal((5000, spec["ndim"])), 0.0, 1.0)
+        return spec, X, "C3: 2-planet ptemcee half-step block, 10 temps x 500 walkers, N(x_true,0.01)"
+    if name == "c5":
+        spec = dict(systems["sys3"])
+        X = rng.random((1_000_000, spec["ndim"]))
+        return spec, X, "C5 chunk: 3-planet system (500 d, dt 0.34874, 1434 steps, 105 obs), 10^6 U(0,1) walkers of the 10^7 sweep"
+    if name != "c4":
+        raise SystemExit(f"unknown workload {name}")
+    base = dict(systems["sys3f"])
+    base["ftime"], base["dt"] = 1500.0, 0.1
+    base["observed"] = {}
+    base["second_term_sum"] = 0.0
+    # pass 1: ephemeris of the true solution over 1500 d on the GPU (untimed set-up)
+    eng = engine_factory(base)
+    n, pl, ep, tm, rs, vs, st = eng.ephemeris(np.array([TRUES_3PL]), mode=2)
+    eng.close()
+    k = int(n[0])
+    pl, ep, tm, rs = pl[0, :k], ep[0, :k], tm[0, :k], rs[0, :k]
+    sig_file = {0: 0.001449, 1: 0.000461, 2: 0.000494}    # Examples/inputs/3pl_planet{1,2,3}_ttvs.dat
+    obs, second = {}, 0.0
+    for pid, idx in base["planets_IDs"].items():
+        m = (pl == idx) & (rs <= base["rstarAU"])
+        sg = float(np.sqrt(2.0) * sig_file[idx])           # planetarysystem.py:325 with lo == hi
+        obs[pid] = {"planet_index": idx, "epochs": [int(e) for e in ep[m]], "times": [float(t) for t in tm[m]],
+                    "sigma": [sg] * int(m.sum())}
+        second += float(np.sum(0.5 * np.log(2 * np.pi * np.full(int(m.sum()), sg) ** 2)))
+    spec = dict(base)
+    spec["observed"] = obs
+    spec["second_term_sum"] = second
+    c = cube_of(spec, TRUES_3PL)
+    X = np.clip(c[None, :] + 0.01 * rng.standard_normal((100_000, spec["ndim"])), 0.0, 1.0)
+    nobs = sum(len(o["epochs"]) for o in obs.values())
+    return spec, X, (f"C4: synthetic 3-planet near-resonant system, 1500 d, dt 0.1 (15001 steps), {nobs} obs, "
+                     "10^5 walkers N(x_true,0.01) per GPU")
+
+
+# ----------------------------------------------------------------------------- CPU side
+def _cpu_worker(args):
+    spec, X = args
+    from oracle import oracle_py
+    osys = oracle_py.OracleSystem(spec)
+    t = time.perf_counter()
+    chi2, logl, st = osys.loglike(X, mode=0)
+    return time.perf_counter() - t, float(np.sum(logl[np.isfinite(logl)]))
+
+
+def cpu_rate(spec, X, budget_s, cores):
+    """Oracle port over `cores` processes on a bounded sample; returns (evals/s, n_sample)."""
+    import multiprocessing as mp
+    from oracle import oracle_py
+    oracle_py.build()
+    osys = oracle_py.OracleSystem(spec)
+    t = time.perf_counter()
+    osys.loglike(X[:4], mode=0)
+    per = max((time.perf_counter() - t) / 4, 1e-5)
+    n = int(max(cores, min(X.shape[0], cores * budget_s / per)))
+    n = (n // cores) * cores
+    chunks = np.array_split(X[:n], cores)
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        pool.map(_cpu_worker, [(spec, c[:2]) for c in chunks])        # warm the workers
+        t = time.perf_counter()
+        pool.map(_cpu_worker, [(spec, c) for c in chunks])
+        wall = time.perf_counter() - t
+    return n / wall, n
+
+
+def run_reference(args):
+    """--impl reference: the CPU implementation of the path on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    systems = load_systems()
+    if args.workload == "c4":
+        # needs the synthetic observed table: built with the oracle itself here (CPU arm)
+        from oracle import oracle_py
+        oracle_py.build()
+        spec, X, desc = make_workload("c4", lambda s: _OracleEngineShim(s))
+    else:
+        spec, X, desc = make_workload(args.workload, None)
+    cores = os.cpu_count() or 1
+    budget = 12.0
+    times = []
+    n = 0
+    for i in range(args.warmup + args.steps):
+        rate, n = cpu_rate(spec, X, budget / max(1, args.steps), cores)
+        if i >= args.warmup:
+            times.append(rate)
+    value = float(np.mean(times))
+    out = {"impl": "reference", "metric": "likelihood evals/sec", "value": value, "unit": "evals/s",
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": 1e3 * n / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f64", "data": "synthetic",
+           "config": {"workload": desc},
+           "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "port",
+                            "sample": f"{n} walkers of the workload per step, oracle C port in {cores} processes"},
+           "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+class _OracleEngineShim:
+    """CPU arm only: gives make_workload('c4') the true-solution ephemeris from the oracle."""
+
+    def __init__(self, spec):
+        self.spec = spec
+
+    def ephemeris(self, X, mode=2):
+        from oracle import oracle_py
+        s = self.spec
+        st, pl, ep, tm, rs, vs = oracle_py.ephemeris(X[0], s["mstar"], s["t0"], s["dt"], s["ftime"])
+        k = len(tm)
+        return (np.array([k]), pl[None, :], ep[None, :], tm[None, :], rs[None, :], vs[None, :], np.array([st]))
+
+    def close(self):
+        pass
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "power_w_max": float(max(pw)), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- GPU side
+def run_gpu(args):
+    import torch
+    import nauyaca_b200 as nb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (nauyaca_b200 has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    spec, X, desc = make_workload(args.workload, lambda s: nb.BatchEngine(s, device=local))
+    # weak scaling: every rank draws its own walkers of the same distribution
+    if world > 1:
+        rng = np.random.default_rng(SEED + rank)
+        if args.workload in ("c2", "c5"):
+            X = rng.random(X.shape)
+        else:
+            c = cube_of(spec, TRUES_3PL if spec["npla"] == 3 else TRUES_2PL)
+            X = np.clip(c[None, :] + 0.01 * rng.standard_normal(X.shape), 0.0, 1.0)
+    B, ndim = X.shape
+    eng = nb.BatchEngine(spec, device=local)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    Xd = torch.from_numpy(X).cuda()
+    chi2 = torch.empty(B, dtype=torch.float64, device="cuda")
+    logl = torch.empty(B, dtype=torch.float64, device="cuda")
+    stat = torch.empty(B, dtype=torch.int32, device="cuda")
+    gathered = torch.empty(world * B, dtype=torch.float64, device="cuda") if world > 1 else None
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+    def step_resident():
+        flush.zero_()
+        eng.loglike_into(Xd.data_ptr(), B, nb.MODE_CUBE, chi2.data_ptr(), logl.data_ptr(), stat.data_ptr(), stream)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, logl)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    launches0 = eng.launch_count()
+    for _ in range(args.warmup):
+        step_resident()
+    sync_all()
+    clocks = ClockSampler(local)
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kernel_ms = []
+    launches_before = eng.launch_count()
+    e0.record()
+    for _ in range(args.steps):
+        step_resident()
+        if args.per_kernel:
+            kernel_ms.append(eng.last_kernel_ms())
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    launches = eng.launch_count() - launches_before
+    # kernel-only duration (CUDA events on the launching stream, recorded inside the ABI call)
+    if not kernel_ms:
+        for _ in range(min(3, args.steps)):
+            step_resident()
+            kernel_ms.append(eng.last_kernel_ms())
+    clk = clocks.stop()
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * B * args.steps / (ms_max * 1e-3)
+
+    # ---- end to end through the public API with HOST buffers (pinned), copies inside
+    Xh = torch.from_numpy(X).pin_memory()
+    logl_h = torch.empty(B, dtype=torch.float64).pin_memory()
+    chi2_h = torch.empty(B, dtype=torch.float64).pin_memory()
+    stat_h = torch.empty(B, dtype=torch.int32).pin_memory()
+
+    def step_e2e():
+        eng.loglike_into(Xh.data_ptr(), B, nb.MODE_CUBE, chi2_h.data_ptr(), logl_h.data_ptr(), stat_h.data_ptr(), stream)
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        step_e2e()
+    sync_all()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        step_e2e()
+    e1.record()
+    sync_all()
+    e2e_ms = max(e0.elapsed_time(e1), 0.0)
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / (float(t.item()) * 1e-3)
+
+    # ---- parity spot-check of what was just timed (host result vs device result, bits)
+    same = bool(np.array_equal(logl_h.numpy(), logl.cpu().numpy(), equal_nan=True))
+
+    if rank == 0:
+        # mean conjunctions per system for the FLOP model, from a 256-system table call
+        n_ev, *_ = eng.ephemeris(eng.cube_to_physical(X[:256])[0], mode=2, cap=1024)
+        nconj = float(np.mean(n_ev))
+        f_eval = flops_per_eval(spec["npla"], eng.nsteps, nconj)
+        kms = float(np.mean(kernel_ms))
+        achieved = f_eval * B / (kms * 1e-3) / 1e12
+        peak = eng.fp64_peak_tflops()
+        nominal = 148 * 64 * 2 * 1.965e9 / 1e12
+        out = {
+            "metric": "likelihood evals/sec", "value": value, "unit": "evals/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": desc, "batch_per_gpu": B, "ndim": ndim, "npla": spec["npla"],
+                       "nsteps": eng.nsteps, "mean_conjunctions": nconj,
+                       "l2": "flushed between steps (256 MiB memset inside the timed region)",
+                       "collective": "all_gather(logl) per step" if world > 1 else "none"},
+            "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": int(B * ndim * 8),
+                    "d2h_bytes_per_step": int(B * (8 + 8 + 4))},
+            "gpu_launches": int(launches),
+            "clocks": clk,
+            "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved / peak if peak else None, "traffic": None,
+                         "peak_source": "FP64 FMA-chain microbenchmark in this run (MEASURED_PEAKS.json has no FP64 entry)",
+                         "nominal_peak": nominal, "frac_of_nominal": achieved / nominal,
+                         "kernel_ms": kms, "flop_per_eval": f_eval,
+                         "hbm": {"algorithmic_bytes_per_launch": int(B * (ndim + 2) * 8 + B * 4),
+                                 "achieved_gbs": (B * (ndim + 2) * 8 + B * 4) / (kms * 1e-3) / 1e9}},
+            "host_device_bits_equal": same,
+        }
+        if world == 1 and not args.no_cpu:
+            cores = os.cpu_count() or 1
+            rate, n = cpu_rate(spec, X, 12.0, cores)
+            out["cpu_baseline"] = {"value": rate, "unit": "evals/s", "cores": cores, "kind": "port",
+                                   "sample": f"first {n} walkers of the same batch, oracle C port in {cores} processes"}
+        print(json.dumps(out))
+    eng.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c4", choices=["c2", "c3", "c4", "c5"])
+    ap.add_argument("--per-kernel", action="store_true", help="read the kernel time after every step (adds a sync)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,149 @@
+/*
+ * ttvb.h -- C ABI of libttvb.so, the B200 (sm_100a) batched TTV likelihood engine.
+ *
+ * Drop-in boundary for ONE path of EliabCanul/nauyaca: flat planetary parameter vector ->
+ * mid-transit ephemerides -> chi-square -> log-likelihood, evaluated for a whole batch of
+ * parameter vectors per call. Plain pointers and sizes only; no C++/torch types.
+ * Every entry point names the reference interface it replaces (paths are relative to the
+ * reference checkout, nauyaca/...).
+ *
+ * Conventions
+ *  - all functions return 0 on success, <0 on error (TTVB_E_*); the message of the last
+ *    error of the calling thread is available from ttvb_last_error(). Nothing throws or
+ *    exits across this boundary.
+ *  - a handle is bound to one CUDA device; calls on one handle are ordered on the stream
+ *    given to the call (NULL = the legacy default stream). One handle per host thread.
+ *  - `x`, and every output array, may be HOST or DEVICE pointers (detected with
+ *    cudaPointerGetAttributes). Host buffers are staged through pinned memory owned by the
+ *    handle and the call returns after the results are in the host arrays. With device
+ *    buffers the call is asynchronous on `stream`.
+ *  - there is NO CPU fallback: without a CUDA device ttvb_create fails with
+ *    TTVB_E_NO_DEVICE.
+ */
+#ifndef TTVB_H
+#define TTVB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TTVB_MAX_PLANETS 9        /* TTVFast MAX_N_PLANETS */
+#define TTVB_EVENT_CAP 5000       /* slots ttvfast-python allocates (utils.py:76-79) */
+
+/* error codes */
+#define TTVB_OK 0
+#define TTVB_E_INVALID (-1)       /* bad argument */
+#define TTVB_E_NO_DEVICE (-2)     /* no CUDA device / device index out of range */
+#define TTVB_E_CUDA (-3)          /* CUDA runtime error, see ttvb_last_error() */
+#define TTVB_E_UNSUPPORTED (-4)   /* npla outside 1..TTVB_MAX_PLANETS */
+
+/* per-system status bits written to status_out */
+#define TTVB_ST_OUT_OF_BOUNDS 1   /* outside hypercube/bounds: chi2=+inf, logl=-inf (utils.py:245-246,368-369) */
+#define TTVB_ST_KEPLER_FAIL 2     /* Kepler drift did not converge; integration stopped, remaining epochs penalised */
+#define TTVB_ST_BAD_TRANSIT 4     /* a transit refinement failed; its time is -1 (TTVFast BAD_TRANSIT) */
+#define TTVB_ST_EVENT_OVERFLOW 8  /* more events than `cap` in ttvb_ephemeris */
+#define TTVB_ST_INVALID_INPUT 16  /* non-finite / non-elliptic elements */
+
+/* interpretation of the rows of `x` */
+#define TTVB_MODE_CUBE 0          /* x[B][ndim] in the unit hypercube: intervals(PS.hypercube) then
+                                     cube_to_physical (utils.py:245-251, 366-374, 403-438) */
+#define TTVB_MODE_PHYSICAL 1      /* x[B][ndim] physical, constants NOT included: intervals(PS.bounds)
+                                     then _insert_constants (utils.py:377-387, 440-447) */
+#define TTVB_MODE_PHYSICAL_FULL 2 /* x[B][7*npla] physical incl. constants, no bounds check
+                                     (calculate_chi2_physical, utils.py:260-330; run_TTVFast :16-81) */
+
+/*
+ * Per-system constants = the attributes of nauyaca.PlanetarySystem consumed by the path
+ * (planetarysystem.py:184-350). All arrays are HOST pointers, copied by ttvb_create.
+ */
+typedef struct ttvb_system {
+    int32_t npla;              /* PS.npla */
+    int32_t ndim;              /* PS.ndim  (= 7*npla - nconst) */
+    int32_t nconst;            /* len(PS.constant_params) */
+    int32_t nobs;              /* total observed transits over all planets */
+    double mstar;              /* PS.mstar [Msun] */
+    double t0, ftime, dt;      /* PS.t0, PS.ftime, PS.dt [days] (planetarysystem.py:266-303) */
+    double rstar_au;           /* PS.rstarAU (planetarysystem.py:204) */
+    double second_term;        /* sum(PS.second_term_logL.values()) (planetarysystem.py:345-348) */
+    const double *bi, *bf;     /* [ndim] PS.bi, PS.bf (planetarysystem.py:213) */
+    const double *cube_lo, *cube_hi;  /* [ndim] PS.hypercube (planetarysystem.py:209) */
+    const double *phys_lo, *phys_hi;  /* [ndim] PS.bounds */
+    const int32_t *const_idx;  /* [nconst] keys of PS.constant_params, ascending flat indices */
+    const double *const_val;   /* [nconst] values of PS.constant_params */
+    const int32_t *obs_planet; /* [nobs] planet index (PS.planets_IDs), grouped by planet */
+    const int32_t *obs_epoch;  /* [nobs] epoch keys of PS.transit_times[planet], table order */
+    const double *obs_time;    /* [nobs] PS.transit_times[planet][epoch] */
+    const double *obs_sigma;   /* [nobs] PS.sigma_obs[planet][epoch] (planetarysystem.py:325) */
+} ttvb_system;
+
+typedef struct ttvb_handle ttvb_handle;
+
+/* Message of the last error raised on the calling thread ("" if none). */
+const char *ttvb_last_error(void);
+
+/* Library/ABI version (major*1000 + minor). */
+int ttvb_version(void);
+
+/* Number of CUDA devices visible (0 if none / no driver). */
+int ttvb_device_count(void);
+
+/*
+ * Upload the constants of one planetary system to `device` and allocate the handle's
+ * workspaces. Replaces the per-call re-pickling of PSystem into the multiprocessing
+ * workers (optimizers.py:185-189, mcmc.py:193-211).
+ */
+int ttvb_create(const ttvb_system *sys, int device, ttvb_handle **out);
+int ttvb_destroy(ttvb_handle *h);
+
+/* Number of integrator steps = iterations of `Time=t0; while(Time<total) Time+=dt` in the
+ * engine behind ttvfast.ttvfast (utils.py:72-74). */
+int ttvb_nsteps(const ttvb_handle *h, int64_t *nsteps);
+
+/*
+ * Batched objective. Replaces, for B vectors at once,
+ *   log_likelihood_func(x, PS, cube, insert_constants)   utils.py:333-399  -> logl_out
+ *   calculate_chi2(x, PS)                                 utils.py:219-257  -> chi2_out
+ *   calculate_chi2_physical(x, PS, individual=...)        utils.py:260-330  -> chi2_out, chi2_planet_out
+ * x: [B][ndim] (modes 0,1) or [B][7*npla] (mode 2), row-major doubles.
+ * chi2_out[B], logl_out[B], status_out[B] : any may be NULL.
+ * chi2_planet_out: NULL or [B][npla] per-planet chi2 (`individual=True`; planets without
+ * observations get 0).
+ */
+int ttvb_loglike(ttvb_handle *h, const double *x, int64_t B, int mode, double *chi2_out,
+                 double *logl_out, double *chi2_planet_out, int32_t *status_out, void *stream);
+
+/*
+ * Batched engine seam. Replaces run_TTVFast(flat, mstar, t0, ftime, dt) (utils.py:16-81),
+ * i.e. ttvfast.ttvfast(..., input_flag=1)['positions'] before the -2 padding, for B vectors.
+ * Outputs are [B][cap] row-major; n_events[B] holds the number of valid leading entries.
+ * Events are ordered by trigger step, planets ascending within a step; epoch counts every
+ * conjunction of that planet (also those with rsky > Rstar).
+ */
+int ttvb_ephemeris(ttvb_handle *h, const double *x, int64_t B, int mode, int32_t cap,
+                   int32_t *n_events, int32_t *planet, int32_t *epoch, double *time, double *rsky,
+                   double *vsky, int32_t *status_out, void *stream);
+
+/*
+ * cube_to_physical(PS, x) (utils.py:403-438) for B vectors: flat_out[B][7*npla].
+ * inside_out (nullable) [B]: 1 if the row is inside PS.hypercube (utils.py:1193-1219).
+ */
+int ttvb_cube_to_physical(ttvb_handle *h, const double *x, int64_t B, double *flat_out,
+                          int32_t *inside_out, void *stream);
+
+/* Device time of the likelihood/ephemeris kernel of the LAST call on this handle, measured
+ * with CUDA events on the call's stream (synchronises on the end event). */
+int ttvb_last_kernel_ms(ttvb_handle *h, float *ms);
+
+/* Number of kernels launched by this handle since creation (bench.py "gpu_launches"). */
+int ttvb_launch_count(const ttvb_handle *h, int64_t *count);
+
+/* FP64 FMA-chain microbenchmark on the handle's device: achieved TFLOP/s (2 flop per FMA).
+ * Used as the measured FP64 roofline denominator (MEASURED_PEAKS.json has no FP64 entry). */
+int ttvb_fp64_peak(ttvb_handle *h, double *tflops, float *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TTVB_H */

@@ -1,0 +1,11 @@
+"""nauyaca_b200 -- B200-native batched TTV likelihood engine behind nauyaca's API.
+
+One hot path only: flat planetary parameter vector -> mid-transit ephemerides ->
+chi-square -> log-likelihood (reference nauyaca/utils.py:16-447), evaluated for whole
+batches on the GPU through the C ABI in include/ttvb.h. No CPU fallback.
+"""
+from ._lib import (MODE_CUBE, MODE_PHYSICAL, MODE_PHYSICAL_FULL, EVENT_CAP, TTVBError, build)
+from .engine import BatchEngine, system_spec
+
+__all__ = ["BatchEngine", "system_spec", "build", "TTVBError", "MODE_CUBE", "MODE_PHYSICAL",
+           "MODE_PHYSICAL_FULL", "EVENT_CAP"]

@@ -1,0 +1,98 @@
+"""ctypes binding of libttvb.so (C ABI in include/ttvb.h) and its in-tree build.
+
+There is no CPU fallback: if the library is missing or no CUDA device is present, calls
+raise. The library is built in-tree by ``build()`` (nvcc, sm_100a) so that it travels with
+the repository snapshot.
+"""
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libttvb.so")
+SRC = os.path.join(_HERE, "csrc", "ttvb.cu")
+DEPS = [SRC, os.path.join(_HERE, "csrc", "ttvb_kernels.cuh"), os.path.join(_HERE, "csrc", "ttvb_math.cuh"),
+        os.path.join(os.path.dirname(_HERE), "include", "ttvb.h")]
+
+# -fmad=false: only the fma() calls written in the source are fused, so the device
+# arithmetic is the same IEEE-754 operation sequence as the CPU oracle's.
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false",
+              "-std=c++17", "-Xcompiler", "-fPIC", "-shared"]
+
+TTVB_OK, TTVB_E_INVALID, TTVB_E_NO_DEVICE, TTVB_E_CUDA, TTVB_E_UNSUPPORTED = 0, -1, -2, -3, -4
+MODE_CUBE, MODE_PHYSICAL, MODE_PHYSICAL_FULL = 0, 1, 2
+ST_OUT_OF_BOUNDS, ST_KEPLER_FAIL, ST_BAD_TRANSIT, ST_EVENT_OVERFLOW, ST_INVALID_INPUT = 1, 2, 4, 8, 16
+EVENT_CAP = 5000
+MAX_PLANETS = 9
+
+EXPORTS = ["ttvb_last_error", "ttvb_version", "ttvb_device_count", "ttvb_create", "ttvb_destroy",
+           "ttvb_nsteps", "ttvb_loglike", "ttvb_ephemeris", "ttvb_cube_to_physical",
+           "ttvb_last_kernel_ms", "ttvb_launch_count", "ttvb_fp64_peak"]
+
+
+class TTVBError(RuntimeError):
+    pass
+
+
+class ttvb_system(C.Structure):
+    _fields_ = [("npla", C.c_int32), ("ndim", C.c_int32), ("nconst", C.c_int32), ("nobs", C.c_int32),
+                ("mstar", C.c_double), ("t0", C.c_double), ("ftime", C.c_double), ("dt", C.c_double),
+                ("rstar_au", C.c_double), ("second_term", C.c_double),
+                ("bi", C.c_void_p), ("bf", C.c_void_p),
+                ("cube_lo", C.c_void_p), ("cube_hi", C.c_void_p),
+                ("phys_lo", C.c_void_p), ("phys_hi", C.c_void_p),
+                ("const_idx", C.c_void_p), ("const_val", C.c_void_p),
+                ("obs_planet", C.c_void_p), ("obs_epoch", C.c_void_p),
+                ("obs_time", C.c_void_p), ("obs_sigma", C.c_void_p)]
+
+
+def needs_build():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in DEPS)
+
+
+def build(force=False, verbose=False):
+    """Compile libttvb.so for sm_100a with nvcc (cross-compiles without a GPU)."""
+    if not force and not needs_build():
+        return LIB_PATH
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, SRC]
+    subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """Load libttvb.so; raises TTVBError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise TTVBError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(nauyaca_b200 has no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    L.ttvb_last_error.restype = C.c_char_p
+    L.ttvb_create.argtypes = [C.POINTER(ttvb_system), C.c_int, C.POINTER(C.c_void_p)]
+    L.ttvb_destroy.argtypes = [C.c_void_p]
+    L.ttvb_nsteps.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+    L.ttvb_loglike.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p,
+                               C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ttvb_ephemeris.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int32, C.c_void_p,
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_void_p]
+    L.ttvb_cube_to_physical.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ttvb_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+    L.ttvb_launch_count.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+    L.ttvb_fp64_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_float)]
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != TTVB_OK:
+        raise TTVBError(f"libttvb error {rc}: {lib().ttvb_last_error().decode()}")

@@ -1,0 +1,485 @@
+// ttvb.cu -- C ABI of libttvb.so (include/ttvb.h) over the sm_100a kernels.
+// No CPU fallback: every entry point needs a CUDA device.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/ttvb.h"
+#include "ttvb_kernels.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(TTVB_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                                  \
+    } while (0)
+
+constexpr long long CHUNK = 1LL << 20;   // systems per launch (bounds staging memory)
+
+}  // namespace
+
+struct ttvb_handle {
+    int device = 0;
+    int num_sms = 0;
+    int blocks_per_sm = 0;
+    ttvb::DevSys sys{};          // host template; per-call fields filled at launch
+    int npla = 0, ndim = 0, nobs = 0;
+    std::vector<double> cube_lo, cube_hi, phys_lo, phys_hi;
+    int* d_obs_epoch = nullptr;
+    double* d_obs_time = nullptr;
+    double* d_obs_sigma = nullptr;
+    unsigned char* d_queue = nullptr;
+    long long queue_stride = 0;
+    int max_grid = 0;
+    // device staging for host-pointer calls (grown on demand)
+    unsigned char* d_stage = nullptr;
+    size_t stage_bytes = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+    long long launches = 0;
+};
+
+namespace {
+
+template <int N>
+int configure(ttvb_handle* h) {
+    // worst-case dynamic shared memory over the three modes
+    size_t smem = ttvb::smem_bytes(N, h->nobs, 7 * N);
+    CU(cudaFuncSetAttribute(ttvb::ttvb_main_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int nb = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ttvb::ttvb_main_kernel<N>, TTVB_TPB, smem));
+    if (nb < 1) return fail(TTVB_E_CUDA, "kernel does not fit on an SM (smem %zu B)", smem);
+    h->blocks_per_sm = nb;
+    h->queue_stride = ttvb::QLayout<N>::BYTES;
+    return TTVB_OK;
+}
+
+template <int N>
+int launch_main(ttvb_handle* h, const ttvb::DevSys& S, int grid, cudaStream_t st) {
+    size_t smem = ttvb::smem_bytes(N, S.nobs, S.rowlen);
+    ttvb::ttvb_main_kernel<N><<<grid, TTVB_TPB, smem, st>>>(S);
+    CU(cudaGetLastError());
+    h->launches++;
+    return TTVB_OK;
+}
+
+int dispatch_configure(ttvb_handle* h) {
+    switch (h->npla) {
+        case 1: return configure<1>(h);
+        case 2: return configure<2>(h);
+        case 3: return configure<3>(h);
+        case 4: return configure<4>(h);
+        case 5: return configure<5>(h);
+        case 6: return configure<6>(h);
+        case 7: return configure<7>(h);
+        case 8: return configure<8>(h);
+        case 9: return configure<9>(h);
+    }
+    return fail(TTVB_E_UNSUPPORTED, "npla=%d outside 1..%d", h->npla, TTVB_MAX_PLANETS);
+}
+
+int dispatch_launch(ttvb_handle* h, const ttvb::DevSys& S, int grid, cudaStream_t st) {
+    switch (h->npla) {
+        case 1: return launch_main<1>(h, S, grid, st);
+        case 2: return launch_main<2>(h, S, grid, st);
+        case 3: return launch_main<3>(h, S, grid, st);
+        case 4: return launch_main<4>(h, S, grid, st);
+        case 5: return launch_main<5>(h, S, grid, st);
+        case 6: return launch_main<6>(h, S, grid, st);
+        case 7: return launch_main<7>(h, S, grid, st);
+        case 8: return launch_main<8>(h, S, grid, st);
+        case 9: return launch_main<9>(h, S, grid, st);
+    }
+    return fail(TTVB_E_UNSUPPORTED, "npla=%d outside 1..%d", h->npla, TTVB_MAX_PLANETS);
+}
+
+bool is_device_ptr(const void* p) {
+    if (p == nullptr) return false;
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+int ensure_stage(ttvb_handle* h, size_t bytes) {
+    if (bytes <= h->stage_bytes) return TTVB_OK;
+    if (h->d_stage) { CU(cudaFree(h->d_stage)); h->d_stage = nullptr; h->stage_bytes = 0; }
+    CU(cudaMalloc(&h->d_stage, bytes));
+    h->stage_bytes = bytes;
+    return TTVB_OK;
+}
+
+void set_mode(ttvb_handle* h, ttvb::DevSys& S, int mode) {
+    S.mode = mode;
+    S.rowlen = (mode == TTVB_MODE_PHYSICAL_FULL) ? 7 * h->npla : h->ndim;
+    const std::vector<double>& lo = (mode == TTVB_MODE_CUBE) ? h->cube_lo : h->phys_lo;
+    const std::vector<double>& hi = (mode == TTVB_MODE_CUBE) ? h->cube_hi : h->phys_hi;
+    for (int i = 0; i < h->ndim; i++) { S.lo[i] = lo[i]; S.hi[i] = hi[i]; }
+}
+
+size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+}  // namespace
+
+extern "C" {
+
+const char* ttvb_last_error(void) { return g_err; }
+
+int ttvb_version(void) { return 1000; }
+
+int ttvb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int ttvb_create(const ttvb_system* sys, int device, ttvb_handle** out) {
+    if (!sys || !out) return fail(TTVB_E_INVALID, "null argument");
+    *out = nullptr;
+    if (sys->npla < 1 || sys->npla > TTVB_MAX_PLANETS)
+        return fail(TTVB_E_UNSUPPORTED, "npla=%d outside 1..%d", sys->npla, TTVB_MAX_PLANETS);
+    if (sys->nconst < 0 || sys->ndim < 0 || sys->ndim + sys->nconst != 7 * sys->npla)
+        return fail(TTVB_E_INVALID, "ndim (%d) + nconst (%d) != 7*npla (%d)", sys->ndim, sys->nconst, 7 * sys->npla);
+    if (sys->nobs < 0) return fail(TTVB_E_INVALID, "nobs < 0");
+    if (!(sys->dt > 0.0) || !std::isfinite(sys->t0) || !std::isfinite(sys->ftime))
+        return fail(TTVB_E_INVALID, "need dt > 0 and finite t0, ftime");
+    int ndev = ttvb_device_count();
+    if (ndev <= 0) return fail(TTVB_E_NO_DEVICE, "no CUDA device available (libttvb has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(TTVB_E_NO_DEVICE, "device %d out of range (0..%d)", device, ndev - 1);
+    CU(cudaSetDevice(device));
+
+    ttvb_handle* h = new (std::nothrow) ttvb_handle();
+    if (!h) return fail(TTVB_E_INVALID, "out of host memory");
+    h->device = device;
+    h->npla = sys->npla; h->ndim = sys->ndim; h->nobs = sys->nobs;
+    ttvb::DevSys& S = h->sys;
+    S.npla = sys->npla; S.ndim = sys->ndim; S.nconst = sys->nconst; S.nobs = sys->nobs;
+    S.gm0 = TTVB_G * sys->mstar;
+    S.t0 = sys->t0; S.dt = sys->dt; S.rstar_au = sys->rstar_au; S.second_term = sys->second_term;
+    // number of steps: same floating-point accumulation as the engine loop
+    {
+        long long n = 0;
+        double T = sys->t0;
+        while (T < sys->ftime) {
+            T += sys->dt; n++;
+            if (n > 2000000000LL) { delete h; return fail(TTVB_E_INVALID, "more than 2e9 steps"); }
+        }
+        S.nsteps = n;
+    }
+    // flat-slot source map (utils.py:440-447: constants inserted at ascending flat indices)
+    {
+        int ic = 0, ix = 0;
+        for (int k = 0; k < 7 * sys->npla; k++) {
+            if (ic < sys->nconst && sys->const_idx[ic] == k) {
+                S.src[k] = -1 - ic; S.cval[ic] = sys->const_val[ic]; ic++;
+            } else {
+                S.src[k] = ix++;
+            }
+        }
+        if (ic != sys->nconst || ix != sys->ndim) {
+            delete h;
+            return fail(TTVB_E_INVALID, "const_idx must be ascending, unique and inside 0..7*npla-1");
+        }
+    }
+    h->cube_lo.resize(sys->ndim); h->cube_hi.resize(sys->ndim);
+    h->phys_lo.resize(sys->ndim); h->phys_hi.resize(sys->ndim);
+    for (int i = 0; i < sys->ndim; i++) {
+        S.bi[i] = sys->bi[i];
+        S.dbf[i] = sys->bf[i] - sys->bi[i];     // utils.py:426 (bf - bi)
+        h->cube_lo[i] = sys->cube_lo[i]; h->cube_hi[i] = sys->cube_hi[i];
+        h->phys_lo[i] = sys->phys_lo[i]; h->phys_hi[i] = sys->phys_hi[i];
+    }
+    // observed table: grouped by planet (ascending), epochs ascending within a planet
+    std::vector<int> order(sys->nobs);
+    for (int i = 0; i < sys->nobs; i++) {
+        order[i] = i;
+        if (sys->obs_planet[i] < 0 || sys->obs_planet[i] >= sys->npla || !(sys->obs_sigma[i] > 0.0)) {
+            delete h;
+            return fail(TTVB_E_INVALID, "observation %d: planet index out of range or sigma <= 0", i);
+        }
+    }
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+        if (sys->obs_planet[a] != sys->obs_planet[b]) return sys->obs_planet[a] < sys->obs_planet[b];
+        return sys->obs_epoch[a] < sys->obs_epoch[b];
+    });
+    std::vector<int> ep(sys->nobs);
+    std::vector<double> tm(sys->nobs), sg(sys->nobs);
+    for (int i = 0; i <= sys->npla; i++) S.obs_start[i] = 0;
+    for (int i = 0; i < sys->nobs; i++) {
+        int o = order[i];
+        ep[i] = sys->obs_epoch[o]; tm[i] = sys->obs_time[o]; sg[i] = sys->obs_sigma[o];
+        S.obs_start[sys->obs_planet[o] + 1]++;
+        if (i > 0 && sys->obs_planet[order[i - 1]] == sys->obs_planet[o] && ep[i - 1] == ep[i]) {
+            delete h;
+            return fail(TTVB_E_INVALID, "duplicate observed epoch %d for planet %d", ep[i], sys->obs_planet[o]);
+        }
+    }
+    for (int i = 0; i < sys->npla; i++) S.obs_start[i + 1] += S.obs_start[i];
+
+    int rc = TTVB_OK;
+    auto bail = [&](int code) { ttvb_destroy(h); return code; };
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(fail(TTVB_E_CUDA, "cudaGetDeviceProperties failed"));
+    h->num_sms = prop.multiProcessorCount;
+    size_t nb = std::max<size_t>(1, sys->nobs);
+    if (cudaMalloc(&h->d_obs_epoch, nb * 4) != cudaSuccess || cudaMalloc(&h->d_obs_time, nb * 8) != cudaSuccess ||
+        cudaMalloc(&h->d_obs_sigma, nb * 8) != cudaSuccess)
+        return bail(fail(TTVB_E_CUDA, "cudaMalloc(observed table) failed: %s", cudaGetErrorString(cudaGetLastError())));
+    if (sys->nobs > 0) {
+        if (cudaMemcpy(h->d_obs_epoch, ep.data(), nb * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(h->d_obs_time, tm.data(), nb * 8, cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(h->d_obs_sigma, sg.data(), nb * 8, cudaMemcpyHostToDevice) != cudaSuccess)
+            return bail(fail(TTVB_E_CUDA, "upload of the observed table failed"));
+    }
+    S.obs_epoch = h->d_obs_epoch; S.obs_time = h->d_obs_time; S.obs_sigma = h->d_obs_sigma;
+    rc = dispatch_configure(h);
+    if (rc != TTVB_OK) return bail(rc);
+    h->max_grid = h->num_sms * h->blocks_per_sm;
+    size_t qbytes = (size_t)h->max_grid * (TTVB_TPB / 32) * (size_t)h->queue_stride;
+    if (cudaMalloc(&h->d_queue, qbytes) != cudaSuccess) return bail(fail(TTVB_E_CUDA, "cudaMalloc(event queues, %zu B) failed", qbytes));
+    S.queue = h->d_queue; S.queue_stride = h->queue_stride;
+    if (cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess)
+        return bail(fail(TTVB_E_CUDA, "cudaEventCreate failed"));
+    *out = h;
+    return TTVB_OK;
+}
+
+int ttvb_destroy(ttvb_handle* h) {
+    if (!h) return TTVB_OK;
+    cudaSetDevice(h->device);
+    if (h->d_obs_epoch) cudaFree(h->d_obs_epoch);
+    if (h->d_obs_time) cudaFree(h->d_obs_time);
+    if (h->d_obs_sigma) cudaFree(h->d_obs_sigma);
+    if (h->d_queue) cudaFree(h->d_queue);
+    if (h->d_stage) cudaFree(h->d_stage);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    delete h;
+    return TTVB_OK;
+}
+
+int ttvb_nsteps(const ttvb_handle* h, int64_t* nsteps) {
+    if (!h || !nsteps) return fail(TTVB_E_INVALID, "null argument");
+    *nsteps = h->sys.nsteps;
+    return TTVB_OK;
+}
+
+// Shared driver of ttvb_loglike / ttvb_ephemeris.
+static int run_batch(ttvb_handle* h, const double* x, int64_t B, int mode, double* chi2_out, double* logl_out,
+                     double* chi2_planet_out, int32_t* status_out, int32_t cap, int32_t* n_events,
+                     int32_t* ev_planet, int32_t* ev_epoch, double* ev_time, double* ev_rsky, double* ev_vsky,
+                     void* stream) {
+    if (!h) return fail(TTVB_E_INVALID, "null handle");
+    if (B < 0) return fail(TTVB_E_INVALID, "B < 0");
+    if (mode < 0 || mode > 2) return fail(TTVB_E_INVALID, "mode %d not in {0,1,2}", mode);
+    if (B == 0) return TTVB_OK;
+    if (!x) return fail(TTVB_E_INVALID, "x is null");
+    const bool table = ev_time != nullptr;
+    if (table && (!n_events || !ev_planet || !ev_epoch || !ev_rsky || !ev_vsky || cap < 1))
+        return fail(TTVB_E_INVALID, "ephemeris outputs must all be non-null and cap >= 1");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool dev = is_device_ptr(x);
+    const void* outs[] = {chi2_out, logl_out, chi2_planet_out, status_out, n_events, ev_planet, ev_epoch, ev_time, ev_rsky, ev_vsky};
+    for (const void* p : outs)
+        if (p && is_device_ptr(p) != dev)
+            return fail(TTVB_E_INVALID, "x and the output arrays must be all host or all device pointers");
+
+    ttvb::DevSys S = h->sys;
+    set_mode(h, S, mode);
+    const int rowlen = S.rowlen, N = h->npla;
+    S.cap = cap;
+    h->timed = false;
+    float total_ms = 0.f;
+    (void)total_ms;
+
+    if (dev) {
+        S.B = B; S.x = x;
+        S.chi2_out = chi2_out; S.logl_out = logl_out; S.chi2_planet_out = chi2_planet_out; S.status_out = status_out;
+        S.n_events = n_events; S.ev_planet = ev_planet; S.ev_epoch = ev_epoch;
+        S.ev_time = ev_time; S.ev_rsky = ev_rsky; S.ev_vsky = ev_vsky;
+        long long ntiles = (B + TTVB_TPB - 1) / TTVB_TPB;
+        int grid = (int)std::min<long long>(ntiles, h->max_grid);
+        CU(cudaEventRecord(h->ev0, st));
+        int rc = dispatch_launch(h, S, grid, st);
+        if (rc != TTVB_OK) return rc;
+        CU(cudaEventRecord(h->ev1, st));
+        h->timed = true;
+        return TTVB_OK;
+    }
+
+    // host pointers: chunked H2D -> kernel -> D2H on `st`, then synchronise
+    const long long chunk = std::min<long long>(B, CHUNK);
+    size_t off_x = 0, bytes = align256((size_t)chunk * rowlen * 8);
+    size_t off_chi2 = bytes; bytes += align256((size_t)chunk * 8);
+    size_t off_logl = bytes; bytes += align256((size_t)chunk * 8);
+    size_t off_pl = bytes;   bytes += align256((size_t)chunk * N * 8);
+    size_t off_st = bytes;   bytes += align256((size_t)chunk * 4);
+    size_t off_ne = bytes, off_ep = 0, off_epo = 0, off_et = 0, off_er = 0, off_ev = 0;
+    if (table) {
+        bytes += align256((size_t)chunk * 4);
+        off_ep = bytes;  bytes += align256((size_t)chunk * cap * 4);
+        off_epo = bytes; bytes += align256((size_t)chunk * cap * 4);
+        off_et = bytes;  bytes += align256((size_t)chunk * cap * 8);
+        off_er = bytes;  bytes += align256((size_t)chunk * cap * 8);
+        off_ev = bytes;  bytes += align256((size_t)chunk * cap * 8);
+    }
+    int rc = ensure_stage(h, bytes);
+    if (rc != TTVB_OK) return rc;
+    unsigned char* d = h->d_stage;
+    CU(cudaEventRecord(h->ev0, st));
+    for (long long b0 = 0; b0 < B; b0 += chunk) {
+        const long long nb = std::min<long long>(chunk, B - b0);
+        CU(cudaMemcpyAsync(d + off_x, x + b0 * rowlen, (size_t)nb * rowlen * 8, cudaMemcpyHostToDevice, st));
+        S.B = nb; S.x = (const double*)(d + off_x);
+        S.chi2_out = chi2_out ? (double*)(d + off_chi2) : nullptr;
+        S.logl_out = logl_out ? (double*)(d + off_logl) : nullptr;
+        S.chi2_planet_out = chi2_planet_out ? (double*)(d + off_pl) : nullptr;
+        S.status_out = status_out ? (int*)(d + off_st) : nullptr;
+        if (table) {
+            S.n_events = (int*)(d + off_ne); S.ev_planet = (int*)(d + off_ep); S.ev_epoch = (int*)(d + off_epo);
+            S.ev_time = (double*)(d + off_et); S.ev_rsky = (double*)(d + off_er); S.ev_vsky = (double*)(d + off_ev);
+        } else {
+            S.n_events = nullptr; S.ev_planet = nullptr; S.ev_epoch = nullptr;
+            S.ev_time = nullptr; S.ev_rsky = nullptr; S.ev_vsky = nullptr;
+        }
+        long long ntiles = (nb + TTVB_TPB - 1) / TTVB_TPB;
+        int grid = (int)std::min<long long>(ntiles, h->max_grid);
+        rc = dispatch_launch(h, S, grid, st);
+        if (rc != TTVB_OK) return rc;
+        if (chi2_out) CU(cudaMemcpyAsync(chi2_out + b0, d + off_chi2, (size_t)nb * 8, cudaMemcpyDeviceToHost, st));
+        if (logl_out) CU(cudaMemcpyAsync(logl_out + b0, d + off_logl, (size_t)nb * 8, cudaMemcpyDeviceToHost, st));
+        if (chi2_planet_out) CU(cudaMemcpyAsync(chi2_planet_out + b0 * N, d + off_pl, (size_t)nb * N * 8, cudaMemcpyDeviceToHost, st));
+        if (status_out) CU(cudaMemcpyAsync(status_out + b0, d + off_st, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
+        if (table) {
+            CU(cudaMemcpyAsync(n_events + b0, d + off_ne, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(ev_planet + b0 * cap, d + off_ep, (size_t)nb * cap * 4, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(ev_epoch + b0 * cap, d + off_epo, (size_t)nb * cap * 4, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(ev_time + b0 * cap, d + off_et, (size_t)nb * cap * 8, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(ev_rsky + b0 * cap, d + off_er, (size_t)nb * cap * 8, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(ev_vsky + b0 * cap, d + off_ev, (size_t)nb * cap * 8, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    CU(cudaEventRecord(h->ev1, st));
+    h->timed = true;
+    CU(cudaStreamSynchronize(st));
+    return TTVB_OK;
+}
+
+int ttvb_loglike(ttvb_handle* h, const double* x, int64_t B, int mode, double* chi2_out, double* logl_out,
+                 double* chi2_planet_out, int32_t* status_out, void* stream) {
+    return run_batch(h, x, B, mode, chi2_out, logl_out, chi2_planet_out, status_out, 0, nullptr, nullptr, nullptr,
+                     nullptr, nullptr, nullptr, stream);
+}
+
+int ttvb_ephemeris(ttvb_handle* h, const double* x, int64_t B, int mode, int32_t cap, int32_t* n_events,
+                   int32_t* planet, int32_t* epoch, double* time, double* rsky, double* vsky, int32_t* status_out,
+                   void* stream) {
+    if (!time) return fail(TTVB_E_INVALID, "time output is null");
+    return run_batch(h, x, B, mode, nullptr, nullptr, nullptr, status_out, cap, n_events, planet, epoch, time, rsky,
+                     vsky, stream);
+}
+
+int ttvb_cube_to_physical(ttvb_handle* h, const double* x, int64_t B, double* flat_out, int32_t* inside_out,
+                          void* stream) {
+    if (!h || !x || !flat_out) return fail(TTVB_E_INVALID, "null argument");
+    if (B <= 0) return B == 0 ? TTVB_OK : fail(TTVB_E_INVALID, "B < 0");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool dev = is_device_ptr(x);
+    if (is_device_ptr(flat_out) != dev || (inside_out && is_device_ptr(inside_out) != dev))
+        return fail(TTVB_E_INVALID, "x and the output arrays must be all host or all device pointers");
+    ttvb::DevSys S = h->sys;
+    set_mode(h, S, TTVB_MODE_CUBE);
+    const int nf = 7 * h->npla;
+    if (dev) {
+        S.B = B; S.x = x;
+        ttvb::ttvb_cube_to_physical_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(S, flat_out, inside_out);
+        CU(cudaGetLastError());
+        h->launches++;
+        return TTVB_OK;
+    }
+    const long long chunk = std::min<long long>(B, CHUNK);
+    size_t bytes = align256((size_t)chunk * h->ndim * 8);
+    size_t off_f = bytes; bytes += align256((size_t)chunk * nf * 8);
+    size_t off_i = bytes; bytes += align256((size_t)chunk * 4);
+    int rc = ensure_stage(h, bytes);
+    if (rc != TTVB_OK) return rc;
+    unsigned char* d = h->d_stage;
+    for (long long b0 = 0; b0 < B; b0 += chunk) {
+        const long long nb = std::min<long long>(chunk, B - b0);
+        CU(cudaMemcpyAsync(d, x + b0 * h->ndim, (size_t)nb * h->ndim * 8, cudaMemcpyHostToDevice, st));
+        S.B = nb; S.x = (const double*)d;
+        ttvb::ttvb_cube_to_physical_kernel<<<(unsigned)((nb + 127) / 128), 128, 0, st>>>(S, (double*)(d + off_f),
+                                                                                       inside_out ? (int*)(d + off_i) : nullptr);
+        CU(cudaGetLastError());
+        h->launches++;
+        CU(cudaMemcpyAsync(flat_out + b0 * nf, d + off_f, (size_t)nb * nf * 8, cudaMemcpyDeviceToHost, st));
+        if (inside_out) CU(cudaMemcpyAsync(inside_out + b0, d + off_i, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaStreamSynchronize(st));
+    return TTVB_OK;
+}
+
+int ttvb_last_kernel_ms(ttvb_handle* h, float* ms) {
+    if (!h || !ms) return fail(TTVB_E_INVALID, "null argument");
+    if (!h->timed) return fail(TTVB_E_INVALID, "no timed call on this handle yet");
+    CU(cudaSetDevice(h->device));
+    CU(cudaEventSynchronize(h->ev1));
+    CU(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+    return TTVB_OK;
+}
+
+int ttvb_launch_count(const ttvb_handle* h, int64_t* count) {
+    if (!h || !count) return fail(TTVB_E_INVALID, "null argument");
+    *count = h->launches;
+    return TTVB_OK;
+}
+
+int ttvb_fp64_peak(ttvb_handle* h, double* tflops, float* ms_out) {
+    if (!h || !tflops) return fail(TTVB_E_INVALID, "null argument");
+    CU(cudaSetDevice(h->device));
+    const int threads = 256, blocks = h->num_sms * 8, iters = 4096;
+    double* d = nullptr;
+    CU(cudaMalloc(&d, (size_t)threads * blocks * 8));
+    cudaEvent_t a, b;
+    CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b));
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; rep++) {
+        CU(cudaEventRecord(a, 0));
+        ttvb::ttvb_fp64_peak_kernel<<<blocks, threads>>>(d, iters, 0.999999, 1e-9);
+        CU(cudaEventRecord(b, 0));
+        CU(cudaEventSynchronize(b));
+        h->launches++;
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, a, b));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    CU(cudaGetLastError());
+    cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(d);
+    double flops = (double)threads * blocks * (double)iters * 64.0 * 2.0;
+    *tflops = flops / (best * 1e-3) / 1e12;
+    if (ms_out) *ms_out = best;
+    return TTVB_OK;
+}
+
+}  // extern "C"

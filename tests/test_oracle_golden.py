@@ -1,0 +1,99 @@
+"""CPU: the oracle against the reference's own known answers (tests/golden)."""
+import math
+
+import numpy as np
+import pytest
+
+TOL_TIME = 1e-7      # days, north-star tolerance against the real TTVFast path
+TOL_CHI2 = 1e-9      # relative
+
+
+def test_nsteps_float_accumulation(oracle):
+    # `Time=t0; while Time<total: Time+=dt`
+    assert oracle.nsteps(0, 221, 0.18) == 1228
+    assert oracle.nsteps(0, 500, 0.34874) == 1434
+    assert oracle.nsteps(0, 1500, 0.1) == 15001
+    assert oracle.nsteps(0, 1359, 0.1) == 13591
+    assert oracle.nsteps(0, 1359, 0.34874) == 3897
+    assert oracle.nsteps(0, 800, 0.75) == 1067
+
+
+@pytest.mark.parametrize("g", ["G1", "G2"])
+def test_golden_ephemerides(oracle, systems, known, g):
+    k = known[g]; s = systems[k["system"]]
+    st, pl, ep, tm, rs, vs = oracle.ephemeris(k["flat_params"], s["mstar"], s["t0"], s["dt"], s["ftime"])
+    assert st == 0
+    for pid, idx in s["planets_IDs"].items():
+        m = (pl == idx) & (rs <= s["rstarAU"])
+        ge = k["ephemeris"][pid]
+        assert list(ep[m]) == ge["epochs"], pid                  # counts and epoch indices exact
+        if ge["times"]:
+            assert np.max(np.abs(tm[m] - np.array(ge["times"]))) <= TOL_TIME
+            assert np.max(np.abs(tm[m] - np.array(ge["times"]))) <= 1e-10   # what the oracle actually reaches
+
+
+def test_g2_masked_conjunctions(oracle, systems, known):
+    # Planet-c of G2 (inc=95 deg): 36 conjunctions, all with rsky > Rstar -> masked (miscellany.ipynb cell 47)
+    k = known["G2"]; s = systems["sys3"]
+    st, pl, ep, tm, rs, vs = oracle.ephemeris(k["flat_params"], s["mstar"], s["t0"], s["dt"], s["ftime"])
+    c = pl == 1
+    assert c.sum() == 36 and np.all(rs[c] > s["rstarAU"])
+    assert list(ep[c]) == list(range(36))
+
+
+@pytest.mark.parametrize("g,tol", [("G1", TOL_CHI2), ("G2", 0.0), ("G3", TOL_CHI2), ("G4", 1e-6)])
+def test_golden_chi2(oracle, systems, known, g, tol):
+    k = known[g]; osys = oracle.OracleSystem(systems[k["system"]])
+    chi2, logl, st = osys.loglike(np.array([k["flat_params"]]), mode=2)
+    assert st[0] == 0
+    assert abs(chi2[0] - k["chi2_current"]) <= tol * k["chi2_current"]
+    assert logl[0] == -0.5 * chi2[0] - osys.second_term
+
+
+def test_g1_individual_chi2_and_logl(oracle, systems, known):
+    k = known["G1"]; s = systems["sys3"]; osys = oracle.OracleSystem(s)
+    st, pl, ep, tm, rs, vs = oracle.ephemeris(k["flat_params"], s["mstar"], s["t0"], s["dt"], s["ftime"])
+    tot, per = osys.chi2_from_events(pl, ep, tm, rs)
+    for i, pid in enumerate(s["planets_IDs"]):
+        ref = k["chi2_individual_old_sigma"][pid] / 2.0          # sigma convention, SURVEY item 5
+        assert abs(per[i] - ref) <= 2e-9 * ref
+    assert tot == (per[0] + per[1]) + per[2]
+
+
+def test_plumbing_cube_to_physical(oracle, systems, plumbing):
+    # bit-exact against outputs of the reference's own cube_to_physical / intervals
+    for name, rows in plumbing.items():
+        osys = oracle.OracleSystem(systems[name])
+        for r in rows:
+            flat = osys.cube_to_physical(np.array(r["cube"]))
+            assert list(flat) == r["physical"]
+            chi2, logl, st = osys.loglike(np.array([r["cube"]]), mode=0)
+            assert bool(st[0] & 1) == (not r["inside"])
+            if not r["inside"]:
+                assert chi2[0] == math.inf and logl[0] == -math.inf
+
+
+def test_deterministic_elementary_functions(oracle):
+    import ctypes as C
+    L = oracle.lib()
+    L.ttvo_test_sincos_deg.argtypes = [C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.ttvo_test_sincos_rad.argtypes = [C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    rng = np.random.default_rng(0)
+    s, c = C.c_double(), C.c_double()
+    worst = 0.0
+    for d in list(rng.uniform(-720, 720, 4000)) + [0.0, 90.0, 180.0, 270.0, 360.0, 45.0, -45.0]:
+        L.ttvo_test_sincos_deg(d, C.byref(s), C.byref(c))
+        r = np.longdouble(d) * (np.pi_ld / np.longdouble(180)) if hasattr(np, "pi_ld") else \
+            np.longdouble(d) * (np.longdouble("3.14159265358979323846264338327950288") / np.longdouble(180))
+        worst = max(worst, abs(float(np.longdouble(s.value) - np.sin(r))), abs(float(np.longdouble(c.value) - np.cos(r))))
+    assert worst < 3e-16
+    L.ttvo_test_sincos_deg(90.0, C.byref(s), C.byref(c)); assert (s.value, c.value) == (1.0, 0.0)
+    L.ttvo_test_sincos_deg(180.0, C.byref(s), C.byref(c)); assert (s.value, c.value) == (0.0, -1.0)
+    worst = 0.0
+    for x in rng.uniform(-7, 7, 4000):
+        L.ttvo_test_sincos_rad(x, C.byref(s), C.byref(c))
+        worst = max(worst, abs(float(np.longdouble(s.value) - np.sin(np.longdouble(x)))),
+                    abs(float(np.longdouble(c.value) - np.cos(np.longdouble(x)))))
+    assert worst < 3e-16
+    for y in list(10 ** rng.uniform(-9, 3, 2000)):
+        assert abs(L.ttvo_test_cbrt(y) - np.cbrt(y)) <= 4.5e-16 * np.cbrt(y)      # 2 ulp
