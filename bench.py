@@ -362,6 +362,12 @@ def run_gpu(args):
         achieved = f_eval * B / (kms * 1e-3) / 1e12
         peak = eng.fp64_peak_tflops()
         nominal = 148 * 64 * 2 * 1.965e9 / 1e12
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+                traffic = json.load(fh).get(args.workload)
+        except Exception:
+            traffic = None
         out = {
             "metric": "likelihood evals/sec", "value": value, "unit": "evals/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
@@ -376,7 +382,9 @@ def run_gpu(args):
             "gpu_launches": int(launches),
             "clocks": clk,
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak if peak else None, "traffic": None,
+                         "frac": achieved / peak if peak else None,
+                         "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
+                         "traffic_source": traffic["source"] if traffic else None,
                          "peak_source": "FP64 FMA-chain microbenchmark in this run (MEASURED_PEAKS.json has no FP64 entry)",
                          "nominal_peak": nominal, "frac_of_nominal": achieved / nominal,
                          "kernel_ms": kms, "flop_per_eval": f_eval,
