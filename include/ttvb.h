@@ -97,6 +97,13 @@ int ttvb_device_count(void);
 int ttvb_create(const ttvb_system *sys, int device, ttvb_handle **out);
 int ttvb_destroy(ttvb_handle *h);
 
+/*
+ * Replace the hypercube bounds used by TTVB_MODE_CUBE. The reference's optimizer shrinks
+ * PSystem.hypercube in place between its global and local stages (optimizers.py:90) while
+ * bi/bf stay fixed; this keeps one handle valid across that mutation. lo, hi: [ndim] host.
+ */
+int ttvb_set_cube_bounds(ttvb_handle *h, const double *lo, const double *hi);
+
 /* Number of integrator steps = iterations of `Time=t0; while(Time<total) Time+=dt` in the
  * engine behind ttvfast.ttvfast (utils.py:72-74). */
 int ttvb_nsteps(const ttvb_handle *h, int64_t *nsteps);

@@ -6,6 +6,9 @@ batches on the GPU through the C ABI in include/ttvb.h. No CPU fallback.
 """
 from ._lib import (MODE_CUBE, MODE_PHYSICAL, MODE_PHYSICAL_FULL, EVENT_CAP, TTVBError, build)
 from .engine import BatchEngine, system_spec
+from . import utils
+from .pool import GpuPool, vectorized_chi2
+from .dist import ShardedEvaluator, shard_bounds
 
-__all__ = ["BatchEngine", "system_spec", "build", "TTVBError", "MODE_CUBE", "MODE_PHYSICAL",
+__all__ = ["BatchEngine", "system_spec", "utils", "GpuPool", "vectorized_chi2", "ShardedEvaluator", "shard_bounds", "build", "TTVBError", "MODE_CUBE", "MODE_PHYSICAL",
            "MODE_PHYSICAL_FULL", "EVENT_CAP"]

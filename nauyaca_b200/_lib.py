@@ -27,7 +27,7 @@ EVENT_CAP = 5000
 MAX_PLANETS = 9
 
 EXPORTS = ["ttvb_last_error", "ttvb_version", "ttvb_device_count", "ttvb_create", "ttvb_destroy",
-           "ttvb_nsteps", "ttvb_loglike", "ttvb_ephemeris", "ttvb_cube_to_physical",
+           "ttvb_set_cube_bounds", "ttvb_nsteps", "ttvb_loglike", "ttvb_ephemeris", "ttvb_cube_to_physical",
            "ttvb_last_kernel_ms", "ttvb_launch_count", "ttvb_fp64_peak"]
 
 
@@ -79,6 +79,7 @@ def lib():
     L.ttvb_last_error.restype = C.c_char_p
     L.ttvb_create.argtypes = [C.POINTER(ttvb_system), C.c_int, C.POINTER(C.c_void_p)]
     L.ttvb_destroy.argtypes = [C.c_void_p]
+    L.ttvb_set_cube_bounds.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.ttvb_nsteps.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
     L.ttvb_loglike.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p,
                                C.c_void_p, C.c_void_p, C.c_void_p]

@@ -277,6 +277,12 @@ int ttvb_destroy(ttvb_handle* h) {
     return TTVB_OK;
 }
 
+int ttvb_set_cube_bounds(ttvb_handle* h, const double* lo, const double* hi) {
+    if (!h || !lo || !hi) return fail(TTVB_E_INVALID, "null argument");
+    for (int i = 0; i < h->ndim; i++) { h->cube_lo[i] = lo[i]; h->cube_hi[i] = hi[i]; }
+    return TTVB_OK;
+}
+
 int ttvb_nsteps(const ttvb_handle* h, int64_t* nsteps) {
     if (!h || !nsteps) return fail(TTVB_E_INVALID, "null argument");
     *nsteps = h->sys.nsteps;
@@ -309,8 +315,6 @@ static int run_batch(ttvb_handle* h, const double* x, int64_t B, int mode, doubl
     const int rowlen = S.rowlen, N = h->npla;
     S.cap = cap;
     h->timed = false;
-    float total_ms = 0.f;
-    (void)total_ms;
 
     if (dev) {
         S.B = B; S.x = x;

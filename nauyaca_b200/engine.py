@@ -88,6 +88,15 @@ class BatchEngine:
         except Exception:
             pass
 
+    def set_cube_bounds(self, hypercube):
+        """Follow an in-place change of PSystem.hypercube (optimizers.py:90)."""
+        lo = np.ascontiguousarray([h[0] for h in hypercube], dtype=np.float64)
+        hi = np.ascontiguousarray([h[1] for h in hypercube], dtype=np.float64)
+        if lo.size != self.ndim:
+            raise ValueError("hypercube must have ndim rows")
+        _lib.check(_lib.lib().ttvb_set_cube_bounds(self._h, lo.ctypes.data, hi.ctypes.data))
+        self._clo, self._chi = lo, hi
+
     # ---------------------------------------------------------------- helpers
     def rowlen(self, mode):
         return 7 * self.npla if mode == MODE_PHYSICAL_FULL else self.ndim

@@ -1,0 +1,86 @@
+"""GPU: the host-side mirror of the reference interface (nauyaca_b200.utils, GpuPool, DE seam)
+through the C ABI, against the goldens and the oracle."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_calculate_ephemeris_golden(systems, known, spec_ps):
+    from nauyaca_b200 import utils as U
+    PS = spec_ps(systems["sys3"])
+    for g in ("G1", "G2"):
+        eph = U.calculate_ephemeris(PS, known[g]["flat_params"])
+        for pid, ge in known[g]["ephemeris"].items():
+            assert list(eph[pid].keys()) == ge["epochs"]
+            if ge["times"]:
+                assert np.max(np.abs(np.array(list(eph[pid].values())) - np.array(ge["times"]))) <= 1e-7
+    SP = U.run_TTVFast(known["G1"]["flat_params"], PS.mstar, init_time=PS.t0, final_time=PS.ftime, dt=PS.dt)
+    assert SP.shape == (5, 105)
+
+
+def test_objectives_match_reference_semantics(systems, known, spec_ps, oracle):
+    from nauyaca_b200 import utils as U
+    spec = systems["sys3"]; PS = spec_ps(spec); osys = oracle.OracleSystem(spec)
+    k = known["G1"]
+    # physical + insert_constants, individual chi2 (miscellany.ipynb cells 20-23, sigma convention /2)
+    ind = U.calculate_chi2_physical(k["phys_free"], PS, insert_constants=True, individual=True)
+    for pid, v in k["chi2_individual_old_sigma"].items():
+        assert abs(ind[pid] - v / 2) <= 2e-9 * v / 2
+    chi2 = U.calculate_chi2_physical(k["phys_free"], PS, insert_constants=True)
+    assert abs(chi2 - k["chi2_current"]) <= 1e-9 * k["chi2_current"]
+    ll = U.log_likelihood_func(k["phys_free"], PS, cube=False, insert_constants=True)
+    assert ll == -0.5 * chi2 - sum(PS.second_term_logL.values())
+    chi2b, eph = U.calculate_chi2_physical(k["flat_params"], PS, get_ephemeris=True)
+    assert chi2b == chi2 and len(eph["Planet-b"]) == 48
+    # G2: 36 missing epochs -> 3.6e21, and the notebook's -inf for the full vector with
+    # cube=False (bounds check misaligned, miscellany.ipynb cells 49-51)
+    assert U.calculate_chi2_physical(known["G2"]["flat_params"], PS) == 3.6e21
+    assert U.log_likelihood_func(known["G2"]["flat_params"], PS, cube=False) == -np.inf
+    with pytest.raises(SystemExit):
+        U.calculate_chi2_physical(k["phys_free"], PS)           # utils.py:309-312
+    # cube objective and bounds
+    x = np.random.default_rng(0).random(spec["ndim"])
+    assert U.calculate_chi2(x, PS) == osys.loglike(x[None, :], mode=0)[0][0]
+    assert U.log_likelihood_func(x, PS) == osys.loglike(x[None, :], mode=0)[1][0]
+    x[3] = 1.0000001
+    assert U.calculate_chi2(x, PS) == np.inf and U.log_likelihood_func(x, PS) == -np.inf
+    assert list(U.cube_to_physical(PS, np.full(spec["ndim"], 0.25))) == list(osys.cube_to_physical(np.full(spec["ndim"], 0.25)))
+
+
+def test_shrunken_hypercube_is_followed(systems, spec_ps):
+    # optimizers.py:90 mutates PSystem.hypercube in place
+    from nauyaca_b200 import utils as U
+    PS = spec_ps(systems["doc2"])
+    x = np.full(PS.ndim, 0.5)
+    assert np.isfinite(U.calculate_chi2(x, PS))
+    PS.hypercube = [[0.6, 0.9]] * PS.ndim
+    assert U.calculate_chi2(x, PS) == np.inf
+    PS.hypercube = [[0.0, 1.0]] * PS.ndim
+    assert np.isfinite(U.calculate_chi2(x, PS))
+
+
+def test_gpupool_and_de_seam_on_gpu(systems, spec_ps, oracle):
+    import nauyaca_b200 as nb
+    from nauyaca_b200 import utils as U
+    from test_host_logic import _Evaluator
+    spec = systems["doc2"]; PS = spec_ps(spec); osys = oracle.OracleSystem(spec)
+    rng = np.random.default_rng(8)
+    P = rng.random((16 * 11, spec["ndim"]))                    # a ptemcee half-step block
+    ev = _Evaluator(U.log_likelihood_func, lambda x: 0.0, [PS, True, False])
+    res = nb.GpuPool().map(ev, list(P))
+    ref = osys.loglike(P, mode=0)[1]
+    assert [r[0] for r in res] == list(ref) and all(r[1] == 0.0 for r in res)
+    # scipy differential evolution, one vectorised generation (optimizers.py:78-83 settings)
+    from scipy.optimize import differential_evolution
+    seen = []
+    f = nb.vectorized_chi2(PS)
+
+    def obj(x):
+        out = f(x)
+        seen.append(np.atleast_1d(out).size)
+        return out
+    r = differential_evolution(obj, PS.hypercube, popsize=30, maxiter=1, mutation=(1.2, 1.7), recombination=0.6,
+                               polish=False, vectorized=True, updating="deferred", seed=1, tol=0.0)
+    assert max(seen) == 30 * spec["ndim"]                       # the whole population in one batch
+    assert np.isfinite(r.fun) and r.fun == osys.loglike(r.x[None, :], mode=0)[0][0]
