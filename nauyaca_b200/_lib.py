@@ -10,7 +10,7 @@ import shutil
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libttvb.so")
+LIB_PATH = os.environ.get("TTVB_LIB") or os.path.join(_HERE, "libttvb.so")   # TTVB_LIB: kernel experiments
 SRC = os.path.join(_HERE, "csrc", "ttvb.cu")
 DEPS = [SRC, os.path.join(_HERE, "csrc", "ttvb_kernels.cuh"), os.path.join(_HERE, "csrc", "ttvb_math.cuh"),
         os.path.join(os.path.dirname(_HERE), "include", "ttvb.h")]

@@ -84,30 +84,38 @@ int launch_main(ttvb_handle* h, const ttvb::DevSys& S, int grid, cudaStream_t st
 
 int dispatch_configure(ttvb_handle* h) {
     switch (h->npla) {
+#ifndef TTVB_DEV_ONLY_23
         case 1: return configure<1>(h);
+#endif
         case 2: return configure<2>(h);
         case 3: return configure<3>(h);
+#ifndef TTVB_DEV_ONLY_23
         case 4: return configure<4>(h);
         case 5: return configure<5>(h);
         case 6: return configure<6>(h);
         case 7: return configure<7>(h);
         case 8: return configure<8>(h);
         case 9: return configure<9>(h);
+#endif
     }
     return fail(TTVB_E_UNSUPPORTED, "npla=%d outside 1..%d", h->npla, TTVB_MAX_PLANETS);
 }
 
 int dispatch_launch(ttvb_handle* h, const ttvb::DevSys& S, int grid, cudaStream_t st) {
     switch (h->npla) {
+#ifndef TTVB_DEV_ONLY_23
         case 1: return launch_main<1>(h, S, grid, st);
+#endif
         case 2: return launch_main<2>(h, S, grid, st);
         case 3: return launch_main<3>(h, S, grid, st);
+#ifndef TTVB_DEV_ONLY_23
         case 4: return launch_main<4>(h, S, grid, st);
         case 5: return launch_main<5>(h, S, grid, st);
         case 6: return launch_main<6>(h, S, grid, st);
         case 7: return launch_main<7>(h, S, grid, st);
         case 8: return launch_main<8>(h, S, grid, st);
         case 9: return launch_main<9>(h, S, grid, st);
+#endif
     }
     return fail(TTVB_E_UNSUPPORTED, "npla=%d outside 1..%d", h->npla, TTVB_MAX_PLANETS);
 }

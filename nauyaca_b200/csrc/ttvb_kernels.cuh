@@ -23,6 +23,9 @@
 
 #define TTVB_MAXFLAT 63   // 7 * TTVB_MAX_PLANETS
 #define TTVB_TPB 128
+#ifndef TTVB_MINB
+#define TTVB_MINB 1
+#endif
 #define TTVB_MAX_PLANETS_P1 10
 #define TTVB_ST_BAD_TRANSIT_BIT 4
 
@@ -72,6 +75,21 @@ struct QLayout {
     static constexpr long long BYTES = 32LL * (NI * 4 + ND * 8);
 };
 
+// per-thread Kepler constants in shared memory: field f of planet i at [(f*N+i)*TPB + tid]
+template <int N>
+struct SmemConsts {
+    double* b;   // base + tid
+    __device__ __forceinline__ double gm(int i) const { return b[(0 * N + i) * TTVB_TPB]; }
+    __device__ __forceinline__ double kc(int i) const { return b[(1 * N + i) * TTVB_TPB]; }
+    __device__ __forceinline__ double q(int i) const { return b[(2 * N + i) * TTVB_TPB]; }
+    __device__ __forceinline__ double ieta(int i) const { return b[(3 * N + i) * TTVB_TPB]; }
+    __device__ __forceinline__ double s(int i) const { return b[(4 * N + i) * TTVB_TPB]; }
+    __device__ __forceinline__ void set(int i, double gm, double kc, double q, double ieta, double s) {
+        b[(0 * N + i) * TTVB_TPB] = gm; b[(1 * N + i) * TTVB_TPB] = kc; b[(2 * N + i) * TTVB_TPB] = q;
+        b[(3 * N + i) * TTVB_TPB] = ieta; b[(4 * N + i) * TTVB_TPB] = s;
+    }
+};
+
 struct WarpQ {
     int* qi;
     double* qd;
@@ -84,7 +102,7 @@ __host__ __device__ inline size_t smem_bytes(int N, int nobs, int rowlen) {
     b = (b + 7) & ~(size_t)7;
     size_t hist = (size_t)2 * 6 * N * TTVB_TPB * 8, stage = (size_t)TTVB_TPB * rowlen * 8;
     b += hist > stage ? hist : stage;                       // history ring / input staging
-    b += (size_t)3 * N * TTVB_TPB * 8;                      // kc, q, gm
+    b += (size_t)5 * N * TTVB_TPB * 8;                      // gm, kc, q, ieta, s
     b += (size_t)N * TTVB_TPB * 8;                          // chi2 accumulators
     b += (size_t)(TTVB_TPB / 32) * 32 * 2 * 8;              // result area (doubles)
     b += (size_t)N * TTVB_TPB * 4;                          // observed-table cursors
@@ -203,29 +221,36 @@ __device__ __forceinline__ void consume_results(const DevSys& S, int cnt, int la
 }
 
 template <int N>
-__global__ void __launch_bounds__(TTVB_TPB)
+__global__ void __launch_bounds__(TTVB_TPB, TTVB_MINB)
 ttvb_main_kernel(const __grid_constant__ DevSys S) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // ---- carve shared memory
-    unsigned char* sp = smem_raw;
-    double* obs_time_s = (double*)sp;  sp += (size_t)S.nobs * 8;
-    double* obs_sigma_s = (double*)sp; sp += (size_t)S.nobs * 8;
-    int* obs_epoch_s = (int*)sp;       sp += (size_t)S.nobs * 4;
-    sp = (unsigned char*)(((uintptr_t)sp + 7) & ~(uintptr_t)7);
-    double* hist = (double*)sp;
-    double* xstage = (double*)sp;      // aliases the ring: only used before the first step
-    {
-        const size_t hb = (size_t)2 * 6 * N * TTVB_TPB * 8, sb = (size_t)TTVB_TPB * S.rowlen * 8;
-        sp += hb > sb ? hb : sb;
-    }
-    double* kc_s = (double*)sp;        sp += (size_t)N * TTVB_TPB * 8;
-    double* q_s = (double*)sp;         sp += (size_t)N * TTVB_TPB * 8;
-    double* gm_s = (double*)sp;        sp += (size_t)N * TTVB_TPB * 8;
-    double* acc_s = (double*)sp;       sp += (size_t)N * TTVB_TPB * 8;
-    double* res_d_all = (double*)sp;   sp += (size_t)(TTVB_TPB / 32) * 32 * 2 * 8;
-    int* cur_s = (int*)sp;             sp += (size_t)N * TTVB_TPB * 4;
-    int* res_i_all = (int*)sp;
+    // ---- carve shared memory (offsets only: no pointer<->integer casts, so that every access
+    //      below is compiled as LDS/STS rather than a generic load/store)
+    // layout: [ring | staging][consts 5N][acc N][res_d][obs_time][obs_sigma] doubles, then
+    //         [cur N][res_i][obs_epoch] ints
+    double* const sd = reinterpret_cast<double*>(smem_raw);
+    const int ring_d = 2 * 6 * N * TTVB_TPB, stage_d = TTVB_TPB * S.rowlen;
+    const int o_cst = ring_d > stage_d ? ring_d : stage_d;
+    const int o_acc = o_cst + 5 * N * TTVB_TPB;
+    const int o_resd = o_acc + N * TTVB_TPB;
+    const int o_obst = o_resd + (TTVB_TPB / 32) * 32 * 2;
+    const int o_obss = o_obst + S.nobs;
+    const int o_int = o_obss + S.nobs;                 // in doubles
+    double* hist = sd;
+    double* xstage = sd;               // aliases the ring: only used before the first step
+    double* cst_s = sd + o_cst;
+    double* gm_s = cst_s;
+    double* kc_s = cst_s + N * TTVB_TPB;
+    double* q_s = cst_s + 2 * N * TTVB_TPB;
+    double* acc_s = sd + o_acc;
+    double* res_d_all = sd + o_resd;
+    double* obs_time_s = sd + o_obst;
+    double* obs_sigma_s = sd + o_obss;
+    int* const si = reinterpret_cast<int*>(smem_raw) + 2 * o_int;
+    int* cur_s = si;
+    int* res_i_all = si + N * TTVB_TPB;
+    int* obs_epoch_s = res_i_all + (TTVB_TPB / 32) * 32 * 4;
 
     for (int i = tid; i < S.nobs; i += TTVB_TPB) {
         obs_time_s[i] = S.obs_time[i];
@@ -258,9 +283,8 @@ ttvb_main_kernel(const __grid_constant__ DevSys S) {
         const long long sys = tile_base + tid;
         bool alive = sys < S.B;
         int status = 0;
-        Consts<N> C;
+        SmemConsts<N> C{cst_s + tid};
         State<N> p;
-        C.gm0 = S.gm0;
         // ---- prologue: bounds, cube->physical, constants, elements -> Jacobi state
         if (alive) {
             const double* xr = xstage + (size_t)tid * rowlen;
@@ -300,7 +324,7 @@ ttvb_main_kernel(const __grid_constant__ DevSys S) {
                 }
                 PlanetInit pi;
                 valid = planet_init(e, S.gm0, eta_prev, pi) && valid;
-                C.gm[i] = pi.gm; C.kc[i] = pi.kc; C.q[i] = pi.q; C.ieta[i] = pi.ieta; C.s[i] = pi.s;
+                C.set(i, pi.gm, pi.kc, pi.q, pi.ieta, pi.s);
 #pragma unroll
                 for (int k = 0; k < 3; k++) {
                     p.x[i][k] = pi.x[k] - R[k];
@@ -308,9 +332,6 @@ ttvb_main_kernel(const __grid_constant__ DevSys S) {
                     R[k] = fma(pi.q, p.x[i][k], R[k]);
                     V[k] = fma(pi.q, p.v[i][k], V[k]);
                 }
-                kc_s[i * TTVB_TPB + tid] = pi.kc;
-                q_s[i * TTVB_TPB + tid] = pi.q;
-                gm_s[i * TTVB_TPB + tid] = pi.gm;
             }
             if (!valid) { status |= 16; alive = false; }
         }
@@ -325,18 +346,7 @@ ttvb_main_kernel(const __grid_constant__ DevSys S) {
             cur_s[i * TTVB_TPB + tid] = S.obs_start[i];
         }
         if (alive) {
-            // third-order corrector as four C(a,b) = A(-a) B(b) A(a) stages
-            const double alpha = 4.18330013267037774e-01, beta = 4.98011920555997350e-02;
-            const double ca = alpha * S.dt, cb = 0.5 * beta * S.dt;
-            bool ok = true;
-#pragma unroll 1
-            for (int sgi = 0; sgi < 4; sgi++) {
-                const double sg = (sgi == 0 || sgi == 3) ? -1.0 : 1.0;
-                const double a = sg * ca, b = sg * cb;
-                ok = map_A<N>(C, p, -a) && ok;
-                map_B<N>(C, p, b);
-                ok = map_A<N>(C, p, a) && ok;
-            }
+            bool ok = corrector<N>(C, p, S.dt);
 #pragma unroll
             for (int i = 0; i < N; i++) prev_dot[i] = sky_g(p.x[i][0], p.x[i][1], p.v[i][0], p.v[i][1]);
             if (ok) ok = map_A<N>(C, p, 0.5 * S.dt);
@@ -359,8 +369,9 @@ ttvb_main_kernel(const __grid_constant__ DevSys S) {
                         hs[(i * 6 + c) * TTVB_TPB] = p.x[i][c];
                         hs[(i * 6 + 3 + c) * TTVB_TPB] = p.v[i][c];
                     }
-                map_B<N>(C, p, S.dt);
-                if (!map_A<N>(C, p, S.dt)) { status |= 2; alive = false; trigmask = 0; }
+                double rj[N], irj[N];
+                map_B<N>(C, p, S.dt, rj, irj);
+                if (!map_A_after_B<N>(C, p, S.dt, rj, irj)) { status |= 2; alive = false; trigmask = 0; }
             }
             Tm2 = Tm1; Tm1 = Time; Time += S.dt;
             // ---- push the events triggered at step k-1 (they now have p_{k-2}, p_{k-1}, p_k)

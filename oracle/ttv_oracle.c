@@ -202,9 +202,10 @@ static void stumpff_G(double alpha, double X, double *G0, double *G1, double *G2
 
 /*
  * Universal-variable Kepler drift of one body about a fixed centre:
- * advance (x,v) by tau under mu. Quartic (Schroeder) Newton on
- *   r0*G1 + u*G2 + mu*G3 = tau,   one reciprocal per iteration,
- * then Gauss f,g in increment form. Returns 0, or ST_KEPLER_FAIL if not converged.
+ * advance (x,v) by tau under mu. Quintic (Schroeder) Newton on
+ *   r0*G1 + u*G2 + mu*G3 = tau,   one reciprocal per iteration, started from a fourth-order
+ * series guess so that one Stumpff evaluation normally suffices, then Gauss f,g in
+ * increment form. Returns 0, or ST_KEPLER_FAIL if not converged.
  */
 static int kepler_drift(double mu, double tau, double *x, double *v)
 {
@@ -216,11 +217,14 @@ static int kepler_drift(double mu, double tau, double *x, double *v)
     double alpha = fma(2.0 * mu, ir0, -v2);
     double zeta = fma(-alpha, r0, mu);
     double au = alpha * u;
-    /* series guess: X = y - A2 y^2 + (2 A2^2 - A3) y^3,  y = tau/r0 */
+    /* fourth-order series guess (reversion of tau/r0 = X + A2 X^2 + A3 X^3 + A4 X^4) */
     double y = tau * ir0;
     double A2 = 0.5 * u * ir0;
     double A3 = fma(mu, ir0, -alpha) * (1.0 / 6.0);
-    double X = y * fma(y, fma(y, fma(2.0 * A2, A2, -A3), -A2), 1.0);
+    double A4 = -au * ir0 * (1.0 / 24.0);
+    double B3 = fma(2.0 * A2, A2, -A3);
+    double B4 = fma(5.0 * A2, fma(A2, A2, -A3), A4);
+    double X = y * fma(y, fma(y, fma(y, -B4, B3), -A2), 1.0);
     double G0, G1, G2, G3, r = 0.0;
     int ok = 0;
     for (int it = 0; it < TTVO_KEP_MAXIT; it++) {
@@ -229,18 +233,23 @@ static int kepler_drift(double mu, double tau, double *x, double *v)
         double F1 = fma(r0, G0, fma(u, G1, mu * G2));
         double F2 = fma(zeta, G1, u * G0);
         double F3 = fma(-au, G1, zeta * G0);
+        double F4 = -alpha * F2;
         double iF1 = 1.0 / F1;
         double h = -F * iF1;
         double b = 0.5 * F2 * iF1;
         double c = F3 * iF1 * (1.0 / 6.0);
-        double d = h * fma(h, fma(h, fma(2.0 * b, b, -c), -b), 1.0);
-        if (fabs(d) <= 1e-5 * fabs(X)) {
-            /* converged: third-order Taylor update of the G functions to X+d */
-            double d2 = 0.5 * d, d3 = d * (1.0 / 3.0);
-            double aG1 = -alpha * G1, aG0 = -alpha * G0;
-            double nG3 = fma(d, fma(d2, fma(d3, G0, G1), G2), G3);
-            double nG2 = fma(d, fma(d2, fma(d3, aG1, G0), G1), G2);
-            double nG1 = fma(d, fma(d2, fma(d3, aG0, aG1), G0), G1);
+        double e4 = F4 * iF1 * (1.0 / 24.0);
+        /* quintic Schroeder step: h - b h^2 + (2b^2-c) h^3 - (5b^3-5bc+e4) h^4 */
+        double k3 = fma(2.0 * b, b, -c);
+        double k4 = fma(5.0 * b, fma(b, b, -c), e4);
+        double d = h * fma(h, fma(h, fma(h, -k4, k3), -b), 1.0);
+        if (fabs(d) <= 2.44140625e-4 * fabs(X)) {
+            /* converged: fourth-order Taylor update of the G functions to X+d */
+            double d2 = 0.5 * d, d3 = d * (1.0 / 3.0), d4 = 0.25 * d;
+            double aG1 = -alpha * G1, aG0 = -alpha * G0, aaG1 = -alpha * aG1;
+            double nG3 = fma(d, fma(d2, fma(d3, fma(d4, aG1, G0), G1), G2), G3);
+            double nG2 = fma(d, fma(d2, fma(d3, fma(d4, aG0, aG1), G0), G1), G2);
+            double nG1 = fma(d, fma(d2, fma(d3, fma(d4, aaG1, aG0), aG1), G0), G1);
             G3 = nG3; G2 = nG2; G1 = nG1;
             G0 = fma(-alpha, G2, 1.0);
             r = fma(r0, G0, fma(u, G1, mu * G2));
@@ -276,7 +285,8 @@ static void over_r3(const double *x, double *w)
 {
     double r2 = dot3(x, x);
     double r = sqrt(r2);
-    double ir3 = 1.0 / (r2 * r);
+    double ir = 1.0 / r;
+    double ir3 = ir * ir * ir;
     w[0] = x[0] * ir3; w[1] = x[1] * ir3; w[2] = x[2] * ir3;
 }
 

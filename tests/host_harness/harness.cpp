@@ -29,7 +29,7 @@ static int run(const double* flat, double mstar, double t0, double dt, double to
         for (int c = 0; c < 7; c++) e[c] = flat[7 * i + c];
         PlanetInit pi;
         valid = planet_init(e, C.gm0, eta_prev, pi) && valid;
-        C.gm[i] = pi.gm; C.kc[i] = pi.kc; C.q[i] = pi.q; C.ieta[i] = pi.ieta; C.s[i] = pi.s;
+        C.gm_[i] = pi.gm; C.kc_[i] = pi.kc; C.q_[i] = pi.q; C.ieta_[i] = pi.ieta; C.s_[i] = pi.s;
         for (int k = 0; k < 3; k++) {
             p.x[i][k] = pi.x[k] - R[k];
             p.v[i][k] = pi.v[k] - V[k];
@@ -38,16 +38,7 @@ static int run(const double* flat, double mstar, double t0, double dt, double to
         }
     }
     if (!valid) return 16;
-    const double alpha = 4.18330013267037774e-01, beta = 4.98011920555997350e-02;
-    const double ca = alpha * dt, cb = 0.5 * beta * dt;
-    bool ok = true;
-    for (int sgi = 0; sgi < 4; sgi++) {
-        const double sg = (sgi == 0 || sgi == 3) ? -1.0 : 1.0;
-        const double a = sg * ca, b = sg * cb;
-        ok = map_A<N>(C, p, -a) && ok;
-        map_B<N>(C, p, b);
-        ok = map_A<N>(C, p, a) && ok;
-    }
+    bool ok = corrector<N>(C, p, dt);
     double prev_dot[N];
     int count[N], trig[N];
     for (int i = 0; i < N; i++) { prev_dot[i] = sky_g(p.x[i][0], p.x[i][1], p.v[i][0], p.v[i][1]); count[i] = 0; trig[i] = 0; }
@@ -57,8 +48,9 @@ static int run(const double* flat, double mstar, double t0, double dt, double to
     double Time = t0, Tm1 = t0, Tm2 = t0;
     for (long long k = 1; k <= nsteps + 1; k++) {
         ring[(k - 1) & 1] = p;
-        map_B<N>(C, p, dt);
-        if (!map_A<N>(C, p, dt)) { status |= 2; break; }
+        double rj[N], irj[N];
+        map_B<N>(C, p, dt, rj, irj);
+        if (!map_A_after_B<N>(C, p, dt, rj, irj)) { status |= 2; break; }
         Tm2 = Tm1; Tm1 = Time; Time += dt;
         for (int i = 0; i < N; i++) {
             if (!trig[i]) continue;
@@ -73,10 +65,10 @@ static int run(const double* flat, double mstar, double t0, double dt, double to
                 double R0 = 0, R1 = 0, R2 = 0, V0 = 0, V1 = 0, V2 = 0;
                 for (int j = 0; j <= i; j++) {
                     double x0 = s.x[j][0], x1 = s.x[j][1], x2 = s.x[j][2], v0 = s.v[j][0], v1 = s.v[j][1], v2 = s.v[j][2];
-                    okk = kepler_drift(C.kc[j], -(0.5 * dt), x0, x1, x2, v0, v1, v2) && okk;
+                    okk = kepler_drift(C.kc(j), -(0.5 * dt), x0, x1, x2, v0, v1, v2) && okk;
                     if (j < i) {
-                        R0 = fma(C.q[j], x0, R0); R1 = fma(C.q[j], x1, R1); R2 = fma(C.q[j], x2, R2);
-                        V0 = fma(C.q[j], v0, V0); V1 = fma(C.q[j], v1, V1); V2 = fma(C.q[j], v2, V2);
+                        R0 = fma(C.q(j), x0, R0); R1 = fma(C.q(j), x1, R1); R2 = fma(C.q(j), x2, R2);
+                        V0 = fma(C.q(j), v0, V0); V1 = fma(C.q(j), v1, V1); V2 = fma(C.q(j), v2, V2);
                     } else {
                         xs[pass][0] = x0 + R0; xs[pass][1] = x1 + R1; xs[pass][2] = x2 + R2;
                         vs2[pass][0] = v0 + V0; vs2[pass][1] = v1 + V1; vs2[pass][2] = v2 + V2;
@@ -87,7 +79,7 @@ static int run(const double* flat, double mstar, double t0, double dt, double to
             }
             double tt, rs, vv;
             if (okk) {
-                const double mu = C.gm0 + C.gm[i];
+                const double mu = C.gm0 + C.gm(i);
                 if (which[1] == 0) okk = locate_bracket(mu, dt, T3[0], T3[1], xs[1], vs2[1], gs[1], xs[0], vs2[0], gs[0], tt, rs, vv);
                 else okk = locate_bracket(mu, dt, T3[1], T3[2], xs[0], vs2[0], gs[0], xs[1], vs2[1], gs[1], tt, rs, vv);
             }
