@@ -36,13 +36,24 @@ TRUES_3PL = [0.07652, 10.4707, 0.0406, 89.809, 292.62, 246.14, 88.3,
 TRUES_2PL = [5.66468, 5.35468, 0.1237, 90.7169039033241, 296.22, 16.39, 88.36,
              26.85598, 11.83319, 0.0727, 90.05186862225226, 187.26, 86.62, 88.95]
 
-# Algorithmic FLOP model of SURVEY.md 8(d) (+,-,*,/,sqrt = 1, FMA = 2)
-F_KEP, F_CHK = 200.0, 6.0
+# Algorithmic FLOP model (+,-,*,/,sqrt = 1, FMA = 2), counted on the canonical arithmetic the
+# kernel and the oracle both execute (DESIGN.md "FLOP table"; SURVEY.md 8(d) gave first
+# estimates of 200 / 25N(N+1)/2+40N / 6, these are the refined constants):
+#   F_KEP  = 185  one universal-variable Kepler drift with the radius handed over by the kick
+#                 (setup 39, Stumpff series 33, quintic step 42, Taylor + f,g update 71);
+#                 +7 (dot3, sqrt, 1/r) when it computes the radius itself
+#   F_R3   = 12   one x/|x|^3  (dot3 5, sqrt 1, 1/r 1, cube 2, scale 3)
+#   F_KICK = 9N + 12(2N-1+P) + 15P + 6N + 6 + 21(N-1) + 12N,  P = N(N-1)/2 pairs
+#   F_CHK  = 3    per planet and step (sky-plane r.v)
+#   F_TR   = 2*((N+1)/2)*192 (synchronise two nodes, mean planet index) + 2*3*211 (two-sided
+#            Newton, 3 iterations of drift + derivative) + 35 (weights, bookkeeping)
+F_KEP, F_KEP_OWN_R, F_R3, F_CHK = 185.0, 192.0, 12.0, 3.0
 
 
 def flops_per_eval(npla, nsteps, nconj):
-    f_kick = 25.0 * npla * (npla + 1) / 2.0 + 40.0 * npla
-    f_tr = 2.0 * npla * F_KEP + 2.0 * 4.0 * (F_KEP + 20.0)
+    P = npla * (npla - 1) / 2.0
+    f_kick = 9 * npla + F_R3 * (2 * npla - 1 + P) + 15 * P + 6 * npla + 6 + 21 * (npla - 1) + 12 * npla
+    f_tr = 2.0 * ((npla + 1) / 2.0) * F_KEP_OWN_R + 2.0 * 3.0 * (F_KEP_OWN_R + 19.0) + 35.0
     return nsteps * (npla * F_KEP + f_kick + npla * F_CHK) + nconj * f_tr
 
 

@@ -14,9 +14,10 @@
  *  - a handle is bound to one CUDA device; calls on one handle are ordered on the stream
  *    given to the call (NULL = the legacy default stream). One handle per host thread.
  *  - `x`, and every output array, may be HOST or DEVICE pointers (detected with
- *    cudaPointerGetAttributes). Host buffers are staged through pinned memory owned by the
- *    handle and the call returns after the results are in the host arrays. With device
- *    buffers the call is asynchronous on `stream`.
+ *    cudaPointerGetAttributes). With host buffers the call copies in chunks (cudaMemcpyAsync
+ *    from/to the caller's buffers; pin them for full PCIe speed) through device staging owned
+ *    by the handle and returns after the results are in the host arrays. With device buffers
+ *    the call is asynchronous on `stream`.
  *  - there is NO CPU fallback: without a CUDA device ttvb_create fails with
  *    TTVB_E_NO_DEVICE.
  */

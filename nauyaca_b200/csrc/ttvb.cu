@@ -13,6 +13,7 @@
 #include "../../include/ttvb.h"
 #include "ttvb_kernels.cuh"
 
+
 namespace {
 
 thread_local char g_err[512] = "";
@@ -53,6 +54,7 @@ struct ttvb_handle {
     // device staging for host-pointer calls (grown on demand)
     unsigned char* d_stage = nullptr;
     size_t stage_bytes = 0;
+    int tpb = TTVB_TPB;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
     long long launches = 0;
@@ -69,6 +71,7 @@ int configure(ttvb_handle* h) {
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ttvb::ttvb_main_kernel<N>, TTVB_TPB, smem));
     if (nb < 1) return fail(TTVB_E_CUDA, "kernel does not fit on an SM (smem %zu B)", smem);
     h->blocks_per_sm = nb;
+    h->tpb = TTVB_TPB;
     h->queue_stride = ttvb::QLayout<N>::BYTES;
     return TTVB_OK;
 }
@@ -262,9 +265,10 @@ int ttvb_create(const ttvb_system* sys, int device, ttvb_handle** out) {
     rc = dispatch_configure(h);
     if (rc != TTVB_OK) return bail(rc);
     h->max_grid = h->num_sms * h->blocks_per_sm;
-    size_t qbytes = (size_t)h->max_grid * (TTVB_TPB / 32) * (size_t)h->queue_stride;
+    size_t qbytes = (size_t)h->max_grid * (h->tpb / 32) * (size_t)h->queue_stride;
     if (cudaMalloc(&h->d_queue, qbytes) != cudaSuccess) return bail(fail(TTVB_E_CUDA, "cudaMalloc(event queues, %zu B) failed", qbytes));
     S.queue = h->d_queue; S.queue_stride = h->queue_stride;
+
     if (cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess)
         return bail(fail(TTVB_E_CUDA, "cudaEventCreate failed"));
     *out = h;
@@ -279,6 +283,7 @@ int ttvb_destroy(ttvb_handle* h) {
     if (h->d_obs_sigma) cudaFree(h->d_obs_sigma);
     if (h->d_queue) cudaFree(h->d_queue);
     if (h->d_stage) cudaFree(h->d_stage);
+
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     delete h;
@@ -329,7 +334,7 @@ static int run_batch(ttvb_handle* h, const double* x, int64_t B, int mode, doubl
         S.chi2_out = chi2_out; S.logl_out = logl_out; S.chi2_planet_out = chi2_planet_out; S.status_out = status_out;
         S.n_events = n_events; S.ev_planet = ev_planet; S.ev_epoch = ev_epoch;
         S.ev_time = ev_time; S.ev_rsky = ev_rsky; S.ev_vsky = ev_vsky;
-        long long ntiles = (B + TTVB_TPB - 1) / TTVB_TPB;
+        long long ntiles = (B + h->tpb - 1) / h->tpb;
         int grid = (int)std::min<long long>(ntiles, h->max_grid);
         CU(cudaEventRecord(h->ev0, st));
         int rc = dispatch_launch(h, S, grid, st);
@@ -374,7 +379,7 @@ static int run_batch(ttvb_handle* h, const double* x, int64_t B, int mode, doubl
             S.n_events = nullptr; S.ev_planet = nullptr; S.ev_epoch = nullptr;
             S.ev_time = nullptr; S.ev_rsky = nullptr; S.ev_vsky = nullptr;
         }
-        long long ntiles = (nb + TTVB_TPB - 1) / TTVB_TPB;
+        long long ntiles = (nb + h->tpb - 1) / h->tpb;
         int grid = (int)std::min<long long>(ntiles, h->max_grid);
         rc = dispatch_launch(h, S, grid, st);
         if (rc != TTVB_OK) return rc;

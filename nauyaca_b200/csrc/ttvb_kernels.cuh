@@ -22,7 +22,9 @@
 #include "ttvb_math.cuh"
 
 #define TTVB_MAXFLAT 63   // 7 * TTVB_MAX_PLANETS
+#ifndef TTVB_TPB
 #define TTVB_TPB 128
+#endif
 #ifndef TTVB_MINB
 #define TTVB_MINB 1
 #endif
