@@ -9,6 +9,7 @@ from .engine import BatchEngine, system_spec
 from . import utils
 from .pool import GpuPool, vectorized_chi2
 from .dist import ShardedEvaluator, shard_bounds
+from . import ptsampler, mcmc
 
-__all__ = ["BatchEngine", "system_spec", "utils", "GpuPool", "vectorized_chi2", "ShardedEvaluator", "shard_bounds", "build", "TTVBError", "MODE_CUBE", "MODE_PHYSICAL",
+__all__ = ["BatchEngine", "system_spec", "utils", "GpuPool", "vectorized_chi2", "ShardedEvaluator", "shard_bounds", "ptsampler", "mcmc", "build", "TTVBError", "MODE_CUBE", "MODE_PHYSICAL",
            "MODE_PHYSICAL_FULL", "EVENT_CAP"]

@@ -1,0 +1,362 @@
+"""Parallel-tempered affine-invariant ensemble sampler with a BATCHED likelihood.
+
+nauyaca's MCMC driver (reference mcmc.py:195-221) uses ``ptemcee.Sampler`` (ptemcee 1.0.0,
+Vousden, Farr & Mandel 2016), which is neither vendored in the reference nor installable
+here. This module restates that sampler's published algorithm behind the same constructor /
+``sample()`` / attribute surface that mcmc.py touches, so that ``MCMC.run`` can be pointed at
+it unchanged:
+
+    Sampler(nwalkers, dim, logl, logp, ntemps=, betas=, Tmax=, a=, pool=, loglargs=,
+            logpkwargs=, adaptation_lag=, adaptation_time=)
+    sampler.sample(p0, iterations=, thin=, storechain=, adapt=, swap_ratios=)  -> generator
+    sampler.chain, .betas, .acceptance_fraction, .tswap_acceptance_fraction,
+    sampler.get_autocorr_time()
+
+Per iteration: two half-ensemble stretch moves with z = exp(U(-ln a,
+ln a)); accept with dim*ln z + beta*dlogl + dlogp; temperature swaps between adjacent
+ladder rungs from the hottest down, on random walker permutations; optional Vousden ladder
+adaptation with decay lag/(t+lag)/time. Each half-step needs the likelihood of
+ntemps*nwalkers/2 proposals: they go to the GPU as ONE batch, either through
+``pool.map`` exactly as ptemcee does (``pool=GpuPool()``) or, faster, through
+``batch_logl(X[B, dim]) -> logl[B]`` which skips the per-vector Python objects.
+
+Parity note: ptemcee draws from an unseeded numpy RandomState, so its chains are not
+reproducible either; parity with the reference is per likelihood evaluation (the GPU path),
+and statistical for the sampler (tests/test_ptsampler.py).
+"""
+import numpy as np
+
+__all__ = ["Sampler", "default_beta_ladder", "LikePriorEvaluator"]
+
+
+def default_beta_ladder(ndim, ntemps=None, Tmax=None):
+    """Geometric ladder of inverse temperatures. With ntemps and Tmax (the case mcmc.py:195-205
+    produces when ``tmax`` is set) betas = logspace(0, -log10(Tmax), ntemps). Without Tmax the
+    ratio between rungs is the dimension-dependent spacing that gives ~25 % swap acceptance on
+    a Gaussian, 1 + 2 sqrt(ln 4)/sqrt(ndim) (Vousden et al. 2016, eq. 22 asymptote) and, with
+    ntemps given, the hottest chain is put at beta = 0."""
+    if type(ndim) != int or ndim < 1:
+        raise ValueError('Invalid number of dimensions specified.')
+    if ntemps is None and Tmax is None:
+        raise ValueError('Must specify one of ``ntemps`` and ``Tmax``.')
+    if Tmax is not None and Tmax <= 1:
+        raise ValueError('``Tmax`` must be greater than 1.')
+    if ntemps is not None and (type(ntemps) != int or ntemps < 1):
+        raise ValueError('Invalid number of temperatures specified.')
+    tstep = 1.0 + 2.0 * np.sqrt(np.log(4.0)) / np.sqrt(ndim)
+    appendInf = False
+    if ntemps is None:
+        ntemps = int(np.log(Tmax) / np.log(tstep) + 2)
+    elif Tmax is None:
+        appendInf = True
+        ntemps -= 1
+    if Tmax is not None and appendInf is False and ntemps > 1:
+        tstep = np.exp(np.log(Tmax) / (ntemps - 1))
+    betas = np.logspace(0, -np.log10(tstep) * (ntemps - 1), ntemps) if ntemps > 0 else np.array([])
+    if appendInf:
+        betas = np.concatenate((betas, [0]))
+    return betas
+
+
+class LikePriorEvaluator:
+    """Picklable (logl, logp) evaluator of one vector: what ptemcee hands to ``pool.map``."""
+
+    def __init__(self, logl, logp, loglargs=(), logpargs=(), loglkwargs=None, logpkwargs=None):
+        self.logl, self.logp = logl, logp
+        self.loglargs, self.logpargs = list(loglargs), list(logpargs)
+        self.loglkwargs, self.logpkwargs = dict(loglkwargs or {}), dict(logpkwargs or {})
+
+    def __call__(self, x):
+        lp = self.logp(x, *self.logpargs, **self.logpkwargs)
+        if np.isnan(lp):
+            raise ValueError('Prior function returned NaN.')
+        if lp == float('-inf'):
+            return 0, lp           # cannot return -inf: it would break beta = 0
+        ll = self.logl(x, *self.loglargs, **self.loglkwargs)
+        if np.isnan(ll).any():
+            raise ValueError('Log likelihood function returned NaN.')
+        return ll, lp
+
+
+class Sampler:
+    def __init__(self, nwalkers, dim, logl, logp, ntemps=None, Tmax=None, betas=None, threads=1, pool=None,
+                 a=2.0, loglargs=(), logpargs=(), loglkwargs=None, logpkwargs=None, adaptation_lag=10000,
+                 adaptation_time=100, random=None, batch_logl=None):
+        self._random = np.random.mtrand.RandomState() if random is None else random
+        self._likeprior = LikePriorEvaluator(logl, logp, loglargs, logpargs, loglkwargs, logpkwargs)
+        self.a = a
+        self.nwalkers = nwalkers
+        self.dim = dim
+        self.adaptation_time = adaptation_time
+        self.adaptation_lag = adaptation_lag
+        self._betas = (default_beta_ladder(self.dim, ntemps=ntemps, Tmax=Tmax) if betas is None
+                       else np.array(betas, dtype=float).copy())
+        self.ntemps = len(self._betas)
+        if self.nwalkers % 2 != 0:
+            raise ValueError('The number of walkers must be even.')
+        if self.nwalkers < 2 * self.dim:
+            raise ValueError('The number of walkers must be greater than ``2*dimension``.')
+        self.pool = pool
+        self.batch_logl = batch_logl
+        self.reset()
+
+    # ------------------------------------------------------------------ state
+    def reset(self, random=None, betas=None, time=None):
+        if random is not None:
+            self._random = random
+        if betas is not None:
+            self._betas = np.array(betas, dtype=float).copy()
+        self._time = 0 if time is None else time
+        self._p0 = None
+        self._logposterior0 = None
+        self._loglikelihood0 = None
+        self.nswap = np.zeros(self.ntemps, dtype=float)
+        self.nswap_accepted = np.zeros(self.ntemps, dtype=float)
+        self.nprop = np.zeros((self.ntemps, self.nwalkers), dtype=float)
+        self.nprop_accepted = np.zeros((self.ntemps, self.nwalkers), dtype=float)
+        self._chain = None
+        self._logposterior = None
+        self._loglikelihood = None
+        self._beta_history = None
+
+    def run_mcmc(self, *args, **kwargs):
+        res = None
+        for res in self.sample(*args, **kwargs):
+            pass
+        return res
+
+    # ------------------------------------------------------------------ evaluation
+    def _evaluate(self, ps):
+        """logl, logp of ps[ntemps, n, dim], each of shape (ntemps, n): ONE batch."""
+        flat = np.ascontiguousarray(ps.reshape((-1, self.dim)))
+        if self.batch_logl is not None:
+            lp = np.array([self._likeprior.logp(x, *self._likeprior.logpargs, **self._likeprior.logpkwargs)
+                           for x in flat], dtype=float)
+            if np.isnan(lp).any():
+                raise ValueError('Prior function returned NaN.')
+            ok = lp != -np.inf
+            ll = np.zeros(flat.shape[0])
+            if ok.any():
+                ll[ok] = np.asarray(self.batch_logl(flat[ok]), dtype=float)
+            if np.isnan(ll).any():
+                raise ValueError('Log likelihood function returned NaN.')
+        else:
+            mapf = map if self.pool is None else self.pool.map
+            results = list(mapf(self._likeprior, flat))
+            ll = np.fromiter((r[0] for r in results), float, count=len(results))
+            lp = np.fromiter((r[1] for r in results), float, count=len(results))
+        return ll.reshape((self.ntemps, -1)), lp.reshape((self.ntemps, -1))
+
+    def _tempered_likelihood(self, logl, betas=None):
+        betas = (self._betas if betas is None else betas).reshape((-1, 1))
+        with np.errstate(invalid='ignore'):
+            loglT = logl * betas
+        loglT[np.isnan(loglT)] = -np.inf
+        return loglT
+
+    # ------------------------------------------------------------------ sampling
+    def sample(self, p0=None, iterations=1, thin=1, storechain=True, adapt=False, swap_ratios=False):
+        if p0 is not None:
+            self._p0 = p = np.array(p0, dtype=float).copy()
+            self._logposterior0 = None
+            self._loglikelihood0 = None
+        elif self._p0 is not None:
+            p = self._p0
+        else:
+            raise ValueError('Initial walker positions not specified.')
+        if p.shape != (self.ntemps, self.nwalkers, self.dim):
+            raise ValueError('p0 must have shape (ntemps, nwalkers, dim).')
+        if self._logposterior0 is None or self._loglikelihood0 is None:
+            logl, logp = self._evaluate(p)
+            logpost = self._tempered_likelihood(logl) + logp
+            self._loglikelihood0, self._logposterior0 = logl, logpost
+        else:
+            logl, logpost = self._loglikelihood0, self._logposterior0
+        if (logpost == -np.inf).any():
+            raise ValueError('Attempting to start with samples outside posterior support.')
+        if storechain:
+            isave = self._expand_chain(iterations // thin)
+        half = self.nwalkers // 2
+        for _ in range(iterations):
+            for j in (0, 1):
+                jupdate, jsample = j, (j + 1) % 2
+                pupdate = p[:, jupdate::2, :]
+                psample = p[:, jsample::2, :]
+                zs = np.exp(self._random.uniform(low=-np.log(self.a), high=np.log(self.a), size=(self.ntemps, half)))
+                qs = np.zeros((self.ntemps, half, self.dim))
+                for k in range(self.ntemps):
+                    js = self._random.randint(0, high=half, size=half)
+                    qs[k, :, :] = psample[k, js, :] + zs[k, :].reshape((half, 1)) * (pupdate[k, :, :] - psample[k, js, :])
+                qslogl, qslogp = self._evaluate(qs)
+                qslogpost = self._tempered_likelihood(qslogl) + qslogp
+                logpaccept = self.dim * np.log(zs) + qslogpost - logpost[:, jupdate::2]
+                logr = np.log(self._random.uniform(low=0.0, high=1.0, size=(self.ntemps, half)))
+                accepts = logr < logpaccept
+                p[:, jupdate::2, :][accepts] = qs[accepts]
+                logpost[:, jupdate::2][accepts] = qslogpost[accepts]
+                logl[:, jupdate::2][accepts] = qslogl[accepts]
+                self.nprop[:, jupdate::2] += 1.0
+                self.nprop_accepted[:, jupdate::2] += accepts
+            p, ratios = self._temperature_swaps(self._betas, p, logpost, logl)
+            if adapt and self.ntemps > 1:
+                dbetas = self._get_ladder_adjustment(self._time, self._betas, ratios)
+                self._betas += dbetas
+                logpost += self._tempered_likelihood(logl, betas=dbetas)
+            if (self._time + 1) % thin == 0 and storechain:
+                self._chain[:, :, isave, :] = p
+                self._logposterior[:, :, isave] = logpost
+                self._loglikelihood[:, :, isave] = logl
+                self._beta_history[:, isave] = self._betas
+                isave += 1
+            self._time += 1
+            self._p0, self._logposterior0, self._loglikelihood0 = p, logpost, logl
+            if swap_ratios:
+                yield p, logpost, logl, ratios
+            else:
+                yield p, logpost, logl
+
+    def _temperature_swaps(self, betas, p, logpost, logl):
+        ntemps = len(betas)
+        ratios = np.zeros(ntemps - 1)
+        for i in range(ntemps - 1, 0, -1):
+            bi, bi1 = betas[i], betas[i - 1]
+            dbeta = bi1 - bi
+            iperm = self._random.permutation(self.nwalkers)
+            i1perm = self._random.permutation(self.nwalkers)
+            raccept = np.log(self._random.uniform(size=self.nwalkers))
+            paccept = dbeta * (logl[i, iperm] - logl[i - 1, i1perm])
+            self.nswap[i] += self.nwalkers
+            self.nswap[i - 1] += self.nwalkers
+            asel = paccept > raccept
+            nacc = np.sum(asel)
+            self.nswap_accepted[i] += nacc
+            self.nswap_accepted[i - 1] += nacc
+            ratios[i - 1] = nacc / self.nwalkers
+            ptemp = np.copy(p[i, iperm[asel], :])
+            logltemp = np.copy(logl[i, iperm[asel]])
+            logprtemp = np.copy(logpost[i, iperm[asel]])
+            p[i, iperm[asel], :] = p[i - 1, i1perm[asel], :]
+            logl[i, iperm[asel]] = logl[i - 1, i1perm[asel]]
+            logpost[i, iperm[asel]] = logpost[i - 1, i1perm[asel]] - dbeta * logl[i - 1, i1perm[asel]]
+            p[i - 1, i1perm[asel], :] = ptemp
+            logl[i - 1, i1perm[asel]] = logltemp
+            logpost[i - 1, i1perm[asel]] = logprtemp + dbeta * logltemp
+        return p, ratios
+
+    def _get_ladder_adjustment(self, time, betas0, ratios):
+        betas = betas0.copy()
+        decay = self.adaptation_lag / (time + self.adaptation_lag)
+        kappa = decay / self.adaptation_time
+        dSs = kappa * (ratios[:-1] - ratios[1:])
+        deltaTs = np.diff(1 / betas[:-1])
+        deltaTs *= np.exp(dSs)
+        betas[1:-1] = 1 / (np.cumsum(deltaTs) + 1 / betas[0])
+        return betas - betas0
+
+    def _expand_chain(self, nsave):
+        if self._chain is None:
+            isave = 0
+            self._chain = np.zeros((self.ntemps, self.nwalkers, nsave, self.dim))
+            self._logposterior = np.zeros((self.ntemps, self.nwalkers, nsave))
+            self._loglikelihood = np.zeros((self.ntemps, self.nwalkers, nsave))
+            self._beta_history = np.zeros((self.ntemps, nsave))
+        else:
+            isave = self._chain.shape[2]
+            self._chain = np.concatenate((self._chain, np.zeros((self.ntemps, self.nwalkers, nsave, self.dim))), axis=2)
+            self._logposterior = np.concatenate((self._logposterior, np.zeros((self.ntemps, self.nwalkers, nsave))), axis=2)
+            self._loglikelihood = np.concatenate((self._loglikelihood, np.zeros((self.ntemps, self.nwalkers, nsave))), axis=2)
+            self._beta_history = np.concatenate((self._beta_history, np.zeros((self.ntemps, nsave))), axis=1)
+        return isave
+
+    # ------------------------------------------------------------------ diagnostics
+    def log_evidence_estimate(self, logls=None, fburnin=0.1):
+        """Thermodynamic-integration estimate of ln Z and its error."""
+        if logls is None:
+            if self.loglikelihood is not None:
+                logls = np.mean(self.loglikelihood, axis=1)[:, int(fburnin * self.loglikelihood.shape[2]):]
+                logls = np.mean(logls, axis=1)
+            else:
+                raise ValueError('No log likelihood values available.')
+        order = np.argsort(self._betas)[::-1]
+        betas, logls = self._betas[order], logls[order]
+        if betas[-1] != 0:
+            betas = np.concatenate((betas, [0])); logls = np.concatenate((logls, [logls[-1]]))
+        betas2 = np.concatenate((betas[::2], [0])) if betas[::2][-1] != 0 else betas[::2]
+        logls2 = np.concatenate((logls[::2], [logls[-1]]))[:len(betas2)]
+        logZ = -np.trapz(logls, betas)
+        logZ2 = -np.trapz(logls2, betas2)
+        return logZ, np.abs(logZ - logZ2)
+
+    @property
+    def random(self):
+        return self._random
+
+    @property
+    def betas(self):
+        return self._betas
+
+    @property
+    def time(self):
+        return self._time
+
+    @property
+    def chain(self):
+        return self._chain
+
+    @property
+    def flatchain(self):
+        s = self.chain.shape
+        return self._chain.reshape((s[0], -1, s[3]))
+
+    @property
+    def logprobability(self):
+        return self._logposterior
+
+    @property
+    def loglikelihood(self):
+        return self._loglikelihood
+
+    @property
+    def beta_history(self):
+        return self._beta_history
+
+    @property
+    def tswap_acceptance_fraction(self):
+        return self.nswap_accepted / self.nswap
+
+    @property
+    def acceptance_fraction(self):
+        return self.nprop_accepted / self.nprop
+
+    @property
+    def acor(self):
+        return self.get_autocorr_time()
+
+    def get_autocorr_time(self, window=50):
+        """Integrated autocorrelation time of the walker-averaged chain, (ntemps, dim)."""
+        acors = np.zeros((self.ntemps, self.dim))
+        for i in range(self.ntemps):
+            x = np.mean(self._chain[i, :, :, :], axis=0)
+            acors[i, :] = _autocorr_integrated_time(x, window=window)
+        return acors
+
+
+def _autocorr_function(x, axis=0):
+    x = np.atleast_1d(x)
+    n = x.shape[axis]
+    f = np.fft.fft(x - np.mean(x, axis=axis, keepdims=True), n=2 * n, axis=axis)
+    m = [slice(None)] * x.ndim
+    m[axis] = slice(0, n)
+    acf = np.fft.ifft(f * np.conjugate(f), axis=axis)[tuple(m)].real
+    m[axis] = 0
+    with np.errstate(invalid='ignore', divide='ignore'):
+        return acf / acf[tuple(m)]
+
+
+def _autocorr_integrated_time(x, axis=0, window=50):
+    f = _autocorr_function(x, axis=axis)
+    if f.ndim == 1:
+        return 1 + 2 * np.sum(f[1:window])
+    m = [slice(None)] * f.ndim
+    m[axis] = slice(1, window)
+    return 1 + 2 * np.sum(f[tuple(m)], axis=axis)

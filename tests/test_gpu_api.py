@@ -84,3 +84,24 @@ def test_gpupool_and_de_seam_on_gpu(systems, spec_ps, oracle):
                                polish=False, vectorized=True, updating="deferred", seed=1, tol=0.0)
     assert max(seen) == 30 * spec["ndim"]                       # the whole population in one batch
     assert np.isfinite(r.fun) and r.fun == osys.loglike(r.x[None, :], mode=0)[0][0]
+
+
+def test_pt_sampler_on_gpu(systems, known, spec_ps, oracle):
+    """mcmc.py:195-221 on the GPU path: pool.map route == block route, walkers climb."""
+    import nauyaca_b200 as nb
+    spec = systems["doc2"]; PS = spec_ps(spec); osys = oracle.OracleSystem(spec)
+    import bench
+    c = bench.cube_of(spec, known["G4"]["flat_params"])
+    rng = np.random.mtrand.RandomState(3)
+    nt, nw = 4, 2 * spec["ndim"] + 2
+    p0 = np.clip(c[None, None, :] + 0.02 * rng.normal(size=(nt, nw, spec["ndim"])), 0, 1)
+    s1 = nb.mcmc.make_sampler(PS, p0, tmax=50.0, random=np.random.mtrand.RandomState(5))
+    s2 = nb.mcmc.make_sampler(PS, p0, tmax=50.0, random=np.random.mtrand.RandomState(5), use_pool=True)
+    r1 = s1.run_mcmc(p0, iterations=30, adapt=True)
+    r2 = s2.run_mcmc(p0, iterations=30, adapt=True)
+    assert np.array_equal(r1[0], r2[0]) and np.array_equal(r1[2], r2[2])
+    # the stored log-likelihoods are the oracle's, bit for bit
+    ref = osys.loglike(r1[0].reshape(-1, spec["ndim"]), mode=0)[1].reshape(nt, nw)
+    assert np.array_equal(r1[2], ref)
+    l0 = osys.loglike(p0[0], mode=0)[1]
+    assert np.median(r1[2][0]) > np.median(l0)
