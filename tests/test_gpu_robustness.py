@@ -1,0 +1,125 @@
+"""GPU: planet counts other than the goldens', hostile inputs, status bits, chunked batches.
+Always GPU (through the C ABI) against the oracle, bit for bit."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _spec(npla, ftime=60.0, dt=0.05, mstar=1.0, nobs_per=6, seed=0):
+    """Synthetic system: all 7*npla parameters free, wide bounds, a small observed table."""
+    rng = np.random.default_rng(seed)
+    ndim = 7 * npla
+    lo = np.tile([0.1, 2.0, 0.0, 80.0, 0.0, 0.0, 0.0], npla).astype(float)
+    hi = np.tile([300.0, 40.0, 0.6, 100.0, 360.0, 360.0, 360.0], npla).astype(float)
+    for i in range(npla):
+        lo[7 * i + 1], hi[7 * i + 1] = 3.0 * 1.7 ** i, 4.0 * 1.7 ** i       # separated periods
+    bi, bf = lo.copy(), hi.copy()
+    for i in range(npla):                                                   # (w+M, w-M) parameterisation
+        bi[7 * i + 4], bf[7 * i + 4] = 0.0, 720.0
+        bi[7 * i + 5], bf[7 * i + 5] = -360.0, 360.0
+    obs = {}
+    for i in range(npla):
+        P = 3.5 * 1.7 ** i
+        ep = list(range(nobs_per))
+        obs[f"p{i}"] = {"planet_index": i, "epochs": ep, "times": [float(1.0 + P * e + 0.01 * rng.normal()) for e in ep],
+                        "sigma": [0.002] * nobs_per}
+    return {"mstar": mstar, "rstarAU": 0.00465 * 1.0, "t0": 0.0, "ftime": ftime, "dt": dt, "npla": npla, "ndim": ndim,
+            "planets_IDs": {f"p{i}": i for i in range(npla)},
+            "bounds": [[float(a), float(b)] for a, b in zip(lo, hi)], "bi": list(map(float, bi)), "bf": list(map(float, bf)),
+            "hypercube": [[0.0, 1.0]] * ndim, "constant_params": {}, "observed": obs, "second_term_sum": 1.25}
+
+
+def _same(a, b):
+    a = np.asarray(a); b = np.asarray(b)
+    ok = (a == b) | (np.isnan(a) & np.isnan(b))
+    assert ok.all(), f"{(~ok).sum()} of {a.size} differ: {a[~ok][:3]} vs {b[~ok][:3]}"
+
+
+@pytest.mark.parametrize("npla", [1, 2, 4, 5])
+def test_other_planet_counts(oracle, npla):
+    import nauyaca_b200 as nb
+    spec = _spec(npla)
+    eng = nb.BatchEngine(spec); osys = oracle.OracleSystem(spec)
+    X = np.random.default_rng(npla).random((200, spec["ndim"]))
+    chi2, logl, st = eng.loglike(X, mode=0)
+    o = osys.loglike(X, mode=0)
+    _same(st, o[2]); _same(chi2, o[0]); _same(logl, o[1])
+    flat, _ = eng.cube_to_physical(X[:16])
+    n, pl, ep, tm, rs, vs, st2 = eng.ephemeris(flat, mode=2, cap=600)
+    for b in range(16):
+        e = oracle.ephemeris(flat[b], spec["mstar"], spec["t0"], spec["dt"], spec["ftime"], cap=600)
+        assert n[b] == len(e[3]) and st2[b] == e[0]
+        _same(tm[b, :n[b]], e[3]); _same(pl[b, :n[b]], e[1]); _same(ep[b, :n[b]], e[2])
+    eng.close()
+
+
+def test_hostile_elements_and_status_bits(oracle):
+    """Huge masses, e up to 0.95, coarse steps: crossing orbits, ejections, Kepler failures.
+    Whatever happens must happen identically in the oracle; nothing aborts the batch."""
+    import nauyaca_b200 as nb
+    spec = _spec(3, ftime=120.0, dt=0.4)
+    eng = nb.BatchEngine(spec); osys = oracle.OracleSystem(spec)
+    rng = np.random.default_rng(99)
+    B = 600
+    flat = np.empty((B, 21))
+    for i in range(3):
+        flat[:, 7 * i + 0] = 10 ** rng.uniform(-1, 4.2, B)          # up to ~16000 Mearth
+        flat[:, 7 * i + 1] = rng.uniform(1.5, 9.0, B)               # overlapping periods
+        flat[:, 7 * i + 2] = rng.uniform(0.0, 0.95, B)
+        flat[:, 7 * i + 3] = rng.uniform(60, 120, B)
+        flat[:, 7 * i + 4:7 * i + 7] = rng.uniform(-400, 800, (B, 3))
+    flat[0, 2] = 1.5                 # invalid eccentricity
+    flat[1, 1] = 0.0                 # invalid period (a = 0)
+    flat[2, 0] = np.nan
+    chi2, logl, st = eng.loglike(flat, mode=2)
+    o = osys.loglike(flat, mode=2)
+    _same(st, o[2]); _same(chi2, o[0]); _same(logl, o[1])
+    assert st[0] & 16 and st[1] & 16 and st[2] & 16
+    assert np.all(np.isfinite(chi2[:2]))                             # penalties, not NaN
+    assert (st & 2).any() and (st & 4).any()                         # the set really is hostile
+    eng.close()
+
+
+def test_event_overflow_bit(oracle):
+    import nauyaca_b200 as nb
+    spec = _spec(2)
+    eng = nb.BatchEngine(spec)
+    X = np.random.default_rng(5).random((8, spec["ndim"]))
+    flat, _ = eng.cube_to_physical(X)
+    n, pl, ep, tm, rs, vs, st = eng.ephemeris(flat, mode=2, cap=5)
+    assert np.all(n == 5) and np.all(st & 8)
+    for b in range(8):
+        e = oracle.ephemeris(flat[b], spec["mstar"], spec["t0"], spec["dt"], spec["ftime"], cap=5)
+        assert e[0] & 8
+        _same(tm[b, :5], e[3])
+    eng.close()
+
+
+def test_identical_walkers_fill_the_queue(oracle):
+    """All 32 lanes of a warp trigger in the same step (identical systems): the event queue
+    takes 32 pushes per planet per step."""
+    import nauyaca_b200 as nb
+    spec = _spec(3)
+    eng = nb.BatchEngine(spec); osys = oracle.OracleSystem(spec)
+    x = np.random.default_rng(1).random(spec["ndim"])
+    X = np.tile(x, (300, 1))
+    chi2, logl, st = eng.loglike(X, mode=0)
+    o = osys.loglike(x[None, :], mode=0)
+    assert np.all(chi2 == o[0][0]) and np.all(st == o[2][0])
+    eng.close()
+
+
+def test_chunked_host_batches(oracle):
+    """More rows than the 2^20 staging chunk: host-pointer path loops over chunks."""
+    import nauyaca_b200 as nb
+    spec = _spec(1, ftime=3.0, dt=0.25, nobs_per=1)
+    eng = nb.BatchEngine(spec); osys = oracle.OracleSystem(spec)
+    B = (1 << 20) + 4097
+    X = np.random.default_rng(2).random((B, spec["ndim"]))
+    chi2, logl, st = eng.loglike(X, mode=0)
+    idx = np.r_[0:50, (1 << 20) - 25:(1 << 20) + 25, B - 50:B]
+    o = osys.loglike(X[idx], mode=0)
+    _same(chi2[idx], o[0]); _same(st[idx], o[2])
+    assert np.isfinite(chi2).all()
+    eng.close()
