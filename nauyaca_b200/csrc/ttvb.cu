@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -55,6 +56,11 @@ struct ttvb_handle {
     unsigned char* d_stage = nullptr;
     size_t stage_bytes = 0;
     int tpb = TTVB_TPB;
+    int* d_sched = nullptr;      // unit counter + per-tile segment flags
+    size_t sched_ints = 0;
+    unsigned char* d_ctx = nullptr;   // hand-over context of time-segmented runs
+    size_t ctx_bytes = 0;
+    int force_nseg = 0;          // TTVB_NSEG (0 = choose per launch)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
     long long launches = 0;
@@ -73,6 +79,55 @@ int configure(ttvb_handle* h) {
     h->blocks_per_sm = nb;
     h->tpb = TTVB_TPB;
     h->queue_stride = ttvb::QLayout<N>::BYTES;
+    return TTVB_OK;
+}
+
+// Work scheduling of one launch. A launch is cut into nseg time segments when that evens out
+// the last, partially filled round of resident CTAs (every system costs the same, so a launch
+// of T tiles on G resident CTAs takes ceil(T/G) rounds; with nseg segments it takes
+// ceil(nseg*T/G)/nseg). Sets S.nseg/seg_len/sched/ctx and returns the grid size.
+int plan_launch(ttvb_handle* h, ttvb::DevSys& S, cudaStream_t st, int* grid_out) {
+    const long long ntiles = (S.B + h->tpb - 1) / h->tpb;
+    const long long G = h->max_grid;
+    int best = 1;
+    if (h->force_nseg > 0) {
+        best = h->force_nseg;
+    } else if (ntiles > G) {
+        double best_eff = (double)ntiles / (double)G / (double)((ntiles + G - 1) / G);
+        for (int s = 2; s <= 8; s++) {
+            if ((S.nsteps + 1) / s < 1000) break;             // keep segments long
+            const long long units = ntiles * s;
+            const double eff = (double)units / (double)G / (double)((units + G - 1) / G);
+            if (eff > best_eff + 0.02) { best_eff = eff; best = s; }
+        }
+    }
+    if ((S.nsteps + 1) / best < 1) best = 1;
+    S.nseg = best;
+    S.seg_len = (S.nsteps + 1 + best - 1) / best;
+    const size_t need_ints = (size_t)ntiles + 1;
+    if (need_ints > h->sched_ints) {
+        if (h->d_sched) CU(cudaFree(h->d_sched));
+        h->d_sched = nullptr; h->sched_ints = 0;
+        CU(cudaMalloc(&h->d_sched, need_ints * 4));
+        h->sched_ints = need_ints;
+    }
+    CU(cudaMemsetAsync(h->d_sched, 0, need_ints * 4, st));
+    S.sched = h->d_sched;
+    S.ctx_d = nullptr; S.ctx_i = nullptr; S.ctx_stride = S.B;
+    if (best > 1) {
+        const size_t nd = 25 * (size_t)h->npla + 3, ni = 2 * (size_t)h->npla + 4;
+        const size_t need = (size_t)S.B * (nd * 8 + ni * 4);
+        if (need > h->ctx_bytes) {
+            if (h->d_ctx) CU(cudaFree(h->d_ctx));
+            h->d_ctx = nullptr; h->ctx_bytes = 0;
+            CU(cudaMalloc(&h->d_ctx, need));
+            h->ctx_bytes = need;
+        }
+        S.ctx_d = (double*)h->d_ctx;
+        S.ctx_i = (int*)(h->d_ctx + (size_t)S.B * nd * 8);
+    }
+    const long long units = ntiles * best;
+    *grid_out = (int)std::min<long long>(units, G);
     return TTVB_OK;
 }
 
@@ -181,6 +236,7 @@ int ttvb_create(const ttvb_system* sys, int device, ttvb_handle** out) {
     ttvb_handle* h = new (std::nothrow) ttvb_handle();
     if (!h) return fail(TTVB_E_INVALID, "out of host memory");
     h->device = device;
+    if (const char* e = std::getenv("TTVB_NSEG")) h->force_nseg = std::atoi(e);   // experiments / tests
     h->npla = sys->npla; h->ndim = sys->ndim; h->nobs = sys->nobs;
     ttvb::DevSys& S = h->sys;
     S.npla = sys->npla; S.ndim = sys->ndim; S.nconst = sys->nconst; S.nobs = sys->nobs;
@@ -283,6 +339,8 @@ int ttvb_destroy(ttvb_handle* h) {
     if (h->d_obs_sigma) cudaFree(h->d_obs_sigma);
     if (h->d_queue) cudaFree(h->d_queue);
     if (h->d_stage) cudaFree(h->d_stage);
+    if (h->d_sched) cudaFree(h->d_sched);
+    if (h->d_ctx) cudaFree(h->d_ctx);
 
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -334,10 +392,11 @@ static int run_batch(ttvb_handle* h, const double* x, int64_t B, int mode, doubl
         S.chi2_out = chi2_out; S.logl_out = logl_out; S.chi2_planet_out = chi2_planet_out; S.status_out = status_out;
         S.n_events = n_events; S.ev_planet = ev_planet; S.ev_epoch = ev_epoch;
         S.ev_time = ev_time; S.ev_rsky = ev_rsky; S.ev_vsky = ev_vsky;
-        long long ntiles = (B + h->tpb - 1) / h->tpb;
-        int grid = (int)std::min<long long>(ntiles, h->max_grid);
+        int grid = 0;
+        int rc = plan_launch(h, S, st, &grid);
+        if (rc != TTVB_OK) return rc;
         CU(cudaEventRecord(h->ev0, st));
-        int rc = dispatch_launch(h, S, grid, st);
+        rc = dispatch_launch(h, S, grid, st);
         if (rc != TTVB_OK) return rc;
         CU(cudaEventRecord(h->ev1, st));
         h->timed = true;
@@ -379,8 +438,9 @@ static int run_batch(ttvb_handle* h, const double* x, int64_t B, int mode, doubl
             S.n_events = nullptr; S.ev_planet = nullptr; S.ev_epoch = nullptr;
             S.ev_time = nullptr; S.ev_rsky = nullptr; S.ev_vsky = nullptr;
         }
-        long long ntiles = (nb + h->tpb - 1) / h->tpb;
-        int grid = (int)std::min<long long>(ntiles, h->max_grid);
+        int grid = 0;
+        rc = plan_launch(h, S, st, &grid);
+        if (rc != TTVB_OK) return rc;
         rc = dispatch_launch(h, S, grid, st);
         if (rc != TTVB_OK) return rc;
         if (chi2_out) CU(cudaMemcpyAsync(chi2_out + b0, d + off_chi2, (size_t)nb * 8, cudaMemcpyDeviceToHost, st));

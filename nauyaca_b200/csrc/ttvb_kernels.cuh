@@ -67,6 +67,15 @@ struct DevSys {
     // per-warp event queues
     unsigned char* queue;
     long long queue_stride;   // bytes per warp
+    // work scheduling: units = (time segment, tile), claimed through sched[0]; sched[1+tile] is
+    // the number of finished segments of a tile. With nseg > 1 a tile's integration is cut into
+    // nseg pieces that different CTAs may run, the per-system context travelling through ctx.
+    int nseg;
+    long long seg_len;        // steps per segment
+    int* sched;
+    double* ctx_d;            // [25N+3][ctx_stride]
+    int* ctx_i;               // [2N+4][ctx_stride]
+    long long ctx_stride;
 };
 
 // ---- queue layout of one warp: 4x32 ints, then (18N+3)x32 doubles
@@ -271,10 +280,67 @@ ttvb_main_kernel(const __grid_constant__ DevSys S) {
     const long long ntiles = (S.B + TTVB_TPB - 1) / TTVB_TPB;
     const int rowlen = S.rowlen;
 
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        __syncthreads();   // previous tile done with shared memory; obs table visible
+    __shared__ int s_unit;
+    const int nunits = (int)ntiles * S.nseg;
+    for (;;) {
+        __syncthreads();   // previous unit done with shared memory; obs table visible
+        if (tid == 0) s_unit = atomicAdd(S.sched, 1);
+        __syncthreads();
+        const int unit = s_unit;
+        if (unit >= nunits) break;
+        const int seg = unit / (int)ntiles;
+        const long long tile = unit - (long long)seg * ntiles;
         const long long tile_base = tile * TTVB_TPB;
-        // ---- coalesced staging of this tile's input rows
+        const long long sys = tile_base + tid;
+        bool alive = sys < S.B;
+        int status = 0;
+        SmemConsts<N> C{cst_s + tid};
+        State<N> p;
+        double prev_dot[N];
+        int count[N];
+        int trigmask = 0, nev = 0;
+        double Time = S.t0, Tm1 = S.t0, Tm2 = S.t0;
+        if (seg > 0) {
+            // ---- resume: wait until the previous segment of this tile is published, reload the context
+            if (tid == 0) {
+                volatile int* flag = S.sched + 1 + tile;
+                while (*flag < seg) __nanosleep(256);
+            }
+            __syncthreads();
+            __threadfence();
+            if (sys < S.B) {
+                const double* cd = S.ctx_d + sys;
+                const int* ci = S.ctx_i + sys;
+                const long long cs = S.ctx_stride;
+                int f = 0;
+#pragma unroll
+                for (int i = 0; i < N; i++)
+#pragma unroll
+                    for (int c = 0; c < 3; c++) { p.x[i][c] = __ldcg(cd + (f++) * cs); }
+#pragma unroll
+                for (int i = 0; i < N; i++)
+#pragma unroll
+                    for (int c = 0; c < 3; c++) { p.v[i][c] = __ldcg(cd + (f++) * cs); }
+                for (int j = 0; j < 12 * N; j++) hist[(size_t)j * TTVB_TPB + tid] = __ldcg(cd + (f++) * cs);
+#pragma unroll
+                for (int i = 0; i < N; i++) prev_dot[i] = __ldcg(cd + (f++) * cs);
+                for (int i = 0; i < N; i++) acc_s[i * TTVB_TPB + tid] = __ldcg(cd + (f++) * cs);
+                for (int j = 0; j < 5 * N; j++) cst_s[(size_t)j * TTVB_TPB + tid] = __ldcg(cd + (f++) * cs);
+                Time = __ldcg(cd + (f++) * cs); Tm1 = __ldcg(cd + (f++) * cs); Tm2 = __ldcg(cd + (f++) * cs);
+                int g = 0;
+#pragma unroll
+                for (int i = 0; i < N; i++) count[i] = __ldcg(ci + (g++) * cs);
+                for (int i = 0; i < N; i++) cur_s[i * TTVB_TPB + tid] = __ldcg(ci + (g++) * cs);
+                trigmask = __ldcg(ci + (g++) * cs);
+                nev = __ldcg(ci + (g++) * cs);
+                status = __ldcg(ci + (g++) * cs);
+                alive = __ldcg(ci + (g++) * cs) != 0;
+            } else {
+#pragma unroll
+                for (int i = 0; i < N; i++) { prev_dot[i] = 0.0; count[i] = 0; }
+            }
+        } else {
+        // ---- first segment: coalesced staging of this tile's input rows, prologue
         {
             const long long nrow = (S.B - tile_base < TTVB_TPB) ? (S.B - tile_base) : TTVB_TPB;
             const long long nel = nrow * rowlen;
@@ -282,11 +348,6 @@ ttvb_main_kernel(const __grid_constant__ DevSys S) {
             for (long long i = tid; i < nel; i += TTVB_TPB) xstage[i] = src[i];
         }
         __syncthreads();
-        const long long sys = tile_base + tid;
-        bool alive = sys < S.B;
-        int status = 0;
-        SmemConsts<N> C{cst_s + tid};
-        State<N> p;
         // ---- prologue: bounds, cube->physical, constants, elements -> Jacobi state
         if (alive) {
             const double* xr = xstage + (size_t)tid * rowlen;
@@ -337,10 +398,6 @@ ttvb_main_kernel(const __grid_constant__ DevSys S) {
             }
             if (!valid) { status |= 16; alive = false; }
         }
-        const bool integrate = (sys < S.B) && !(status & 1);   // out of bounds: chi2=+inf
-        double prev_dot[N];
-        int count[N];
-        int trigmask = 0, nev = 0;
 #pragma unroll
         for (int i = 0; i < N; i++) {
             prev_dot[i] = 0.0; count[i] = 0;
@@ -354,13 +411,16 @@ ttvb_main_kernel(const __grid_constant__ DevSys S) {
             if (ok) ok = map_A<N>(C, p, 0.5 * S.dt);
             if (!ok) { status |= 2; alive = false; }
         }
-        // ---- integration
-        double Time = S.t0, Tm1 = S.t0, Tm2 = S.t0;
+        }   // seg == 0
+        const bool integrate = (sys < S.B) && !(status & 1);   // out of bounds: chi2=+inf
+        // ---- integration of steps k0..k1 of this unit
+        const long long k0 = (long long)seg * S.seg_len + 1;
+        const long long k1 = (seg == S.nseg - 1) ? (S.nsteps + 1) : (long long)(seg + 1) * S.seg_len;
         int qcount = 0;
         const int warp_base_tid = warp * 32;
         const long long warp_base_sys = tile_base + warp_base_tid;
 #pragma unroll 1
-        for (long long k = 1; k <= S.nsteps + 1; k++) {
+        for (long long k = k0; k <= k1; k++) {
             if (__ballot_sync(0xffffffffu, alive) == 0u) break;
             if (alive) {
                 double* hs = hist + (size_t)((k - 1) & 1) * 6 * N * TTVB_TPB + tid;
@@ -444,6 +504,41 @@ ttvb_main_kernel(const __grid_constant__ DevSys S) {
                 process_batch<N>(S, cnt, Q, kc_s, q_s, gm_s, res_i, res_d, warp_base_tid, warp_base_sys);
                 consume_results(S, cnt, lane, tid, res_i, res_d, obs_epoch_s, obs_time_s, obs_sigma_s, acc_s, cur_s, status);
             }
+        }
+        if (seg < S.nseg - 1) {
+            // ---- hand the tile over: save the context, publish the segment
+            if (sys < S.B) {
+                double* cd = S.ctx_d + sys;
+                int* ci = S.ctx_i + sys;
+                const long long cs = S.ctx_stride;
+                int f = 0;
+#pragma unroll
+                for (int i = 0; i < N; i++)
+#pragma unroll
+                    for (int c = 0; c < 3; c++) { cd[(f++) * cs] = p.x[i][c]; }
+#pragma unroll
+                for (int i = 0; i < N; i++)
+#pragma unroll
+                    for (int c = 0; c < 3; c++) { cd[(f++) * cs] = p.v[i][c]; }
+                for (int j = 0; j < 12 * N; j++) cd[(f++) * cs] = hist[(size_t)j * TTVB_TPB + tid];
+#pragma unroll
+                for (int i = 0; i < N; i++) cd[(f++) * cs] = prev_dot[i];
+                for (int i = 0; i < N; i++) cd[(f++) * cs] = acc_s[i * TTVB_TPB + tid];
+                for (int j = 0; j < 5 * N; j++) cd[(f++) * cs] = cst_s[(size_t)j * TTVB_TPB + tid];
+                cd[(f++) * cs] = Time; cd[(f++) * cs] = Tm1; cd[(f++) * cs] = Tm2;
+                int g = 0;
+#pragma unroll
+                for (int i = 0; i < N; i++) ci[(g++) * cs] = count[i];
+                for (int i = 0; i < N; i++) ci[(g++) * cs] = cur_s[i * TTVB_TPB + tid];
+                ci[(g++) * cs] = trigmask;
+                ci[(g++) * cs] = nev;
+                ci[(g++) * cs] = status;
+                ci[(g++) * cs] = alive ? 1 : 0;
+            }
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) atomicExch(S.sched + 1 + tile, seg + 1);
+            continue;
         }
         // ---- epilogue: remaining observed epochs are missing -> penalty; totals
         if (sys < S.B) {
