@@ -415,6 +415,78 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+def run_c3(args):
+    """BASELINE configs[2]: the ptemcee-style MCMC itself. A step = one full PT iteration of
+    10 temperatures x 1000 walkers (two half-ensemble stretch moves of 5000 proposals each,
+    temperature swaps, ladder adaptation) through nauyaca_b200.mcmc.make_sampler; host sampler
+    work and the host<->device copies of every half-step are inside the timed region, so
+    value == e2e. With N > 1 every rank runs an independent replica of the ensemble (a
+    5000-proposal block is latency-bound on one GPU: sharding it does not shorten the step)."""
+    import torch
+    import nauyaca_b200 as nb
+    from tests.conftest import SpecPS
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    nb.utils.DEFAULT_DEVICE = local
+    spec = dict(load_systems()["doc2"])
+    spec.setdefault("second_term_logL", {"all": spec["second_term_sum"]})
+    PS = SpecPS(spec)
+    nt, nw = 10, 1000
+    rng = np.random.mtrand.RandomState(SEED + rank)
+    c = cube_of(spec, TRUES_2PL)
+    p0 = np.clip(c[None, None, :] + 0.01 * rng.normal(size=(nt, nw, spec["ndim"])), 0.0, 1.0)
+    sampler = nb.mcmc.make_sampler(PS, p0, tmax=100.0, random=rng)
+    eng = nb.utils.engine_for(PS, device=local)
+    it = sampler.sample(p0, iterations=args.warmup + args.steps, thin=1, storechain=False, adapt=True)
+    for _ in range(args.warmup):
+        next(it)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = ClockSampler(local); clocks.start()
+    l0 = eng.launch_count()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        p, logpost, logl = next(it)
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) * 1e3
+    launches = eng.launch_count() - l0
+    kms = eng.last_kernel_ms()
+    clk = clocks.stop()
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    evals = world * args.steps * nt * nw
+    if rank == 0:
+        B = nt * nw // 2
+        f_eval = flops_per_eval(spec["npla"], eng.nsteps, 60.0)
+        value = evals / (ms * 1e-3)
+        peak = eng.fp64_peak_tflops()
+        achieved = f_eval * B / (kms * 1e-3) / 1e12
+        out = {"metric": "likelihood evals/sec", "value": value, "unit": "evals/s", "n_gpus": world,
+               "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+               "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": {"workload": "C3: ptemcee-style PT MCMC, 2-planet system (1228 steps, 60 obs), 10 temperatures x 1000 "
+                                      "walkers, one PT iteration per step (2 x 5000 proposals), independent replica per GPU",
+                          "mean_logl_cold": float(np.mean(logl[0])), "swap_fraction_cold": float(sampler.tswap_acceptance_fraction[0]),
+                          "l2": "not flushed: a 5000-proposal block is 0.5 MB and latency-bound"},
+               "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": int(2 * B * spec["ndim"] * 8),
+                       "d2h_bytes_per_step": int(2 * B * 20)},
+               "gpu_launches": int(launches), "clocks": clk,
+               "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                            "frac": achieved / peak, "traffic": None, "kernel_ms": kms, "flop_per_eval": f_eval,
+                            "note": "latency-bound: 157 warps on 592 schedulers"}}
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier(); dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -427,6 +499,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "c3":
+        run_c3(args)
     else:
         run_gpu(args)
 

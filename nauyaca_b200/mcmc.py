@@ -44,7 +44,9 @@ def make_sampler(PSystem, p0, betas=None, tmax=None, logprior=None, evaluate=Non
     if evaluate is None:
         def evaluate(X):
             return _u.log_likelihood_batch(X, PSystem, cube=p0_norm, insert_constants=insert_cnst)
-    return Sampler(batch_logl=evaluate, **kw)
+    # the reference's default prior is identically 0.0 (mcmc.py:505-509): no per-vector calls
+    blp = (lambda X: np.zeros(X.shape[0])) if logprior is None else None
+    return Sampler(batch_logl=evaluate, batch_logp=blp, **kw)
 
 
 def pt_sample(PSystem, p0, iterations, thin=1, **kw):

@@ -18,7 +18,9 @@ ladder rungs from the hottest down, on random walker permutations; optional Vous
 adaptation with decay lag/(t+lag)/time. Each half-step needs the likelihood of
 ntemps*nwalkers/2 proposals: they go to the GPU as ONE batch, either through
 ``pool.map`` exactly as ptemcee does (``pool=GpuPool()``) or, faster, through
-``batch_logl(X[B, dim]) -> logl[B]`` which skips the per-vector Python objects.
+``batch_logl(X[B, dim]) -> logl[B]`` which skips the per-vector Python objects (and
+``batch_logp`` for a vectorised prior; the per-vector prior loop costs more than the GPU
+kernel at 5000 proposals per half-step).
 
 Parity note: ptemcee draws from an unseeded numpy RandomState, so its chains are not
 reproducible either; parity with the reference is per likelihood evaluation (the GPU path),
@@ -81,7 +83,7 @@ class LikePriorEvaluator:
 class Sampler:
     def __init__(self, nwalkers, dim, logl, logp, ntemps=None, Tmax=None, betas=None, threads=1, pool=None,
                  a=2.0, loglargs=(), logpargs=(), loglkwargs=None, logpkwargs=None, adaptation_lag=10000,
-                 adaptation_time=100, random=None, batch_logl=None):
+                 adaptation_time=100, random=None, batch_logl=None, batch_logp=None):
         self._random = np.random.mtrand.RandomState() if random is None else random
         self._likeprior = LikePriorEvaluator(logl, logp, loglargs, logpargs, loglkwargs, logpkwargs)
         self.a = a
@@ -98,6 +100,7 @@ class Sampler:
             raise ValueError('The number of walkers must be greater than ``2*dimension``.')
         self.pool = pool
         self.batch_logl = batch_logl
+        self.batch_logp = batch_logp      # optional vectorised prior X[B, dim] -> logp[B]
         self.reset()
 
     # ------------------------------------------------------------------ state
@@ -130,8 +133,11 @@ class Sampler:
         """logl, logp of ps[ntemps, n, dim], each of shape (ntemps, n): ONE batch."""
         flat = np.ascontiguousarray(ps.reshape((-1, self.dim)))
         if self.batch_logl is not None:
-            lp = np.array([self._likeprior.logp(x, *self._likeprior.logpargs, **self._likeprior.logpkwargs)
-                           for x in flat], dtype=float)
+            if self.batch_logp is not None:
+                lp = np.asarray(self.batch_logp(flat), dtype=float)
+            else:
+                lp = np.array([self._likeprior.logp(x, *self._likeprior.logpargs, **self._likeprior.logpkwargs)
+                               for x in flat], dtype=float)
             if np.isnan(lp).any():
                 raise ValueError('Prior function returned NaN.')
             ok = lp != -np.inf
@@ -183,10 +189,10 @@ class Sampler:
                 pupdate = p[:, jupdate::2, :]
                 psample = p[:, jsample::2, :]
                 zs = np.exp(self._random.uniform(low=-np.log(self.a), high=np.log(self.a), size=(self.ntemps, half)))
-                qs = np.zeros((self.ntemps, half, self.dim))
-                for k in range(self.ntemps):
-                    js = self._random.randint(0, high=half, size=half)
-                    qs[k, :, :] = psample[k, js, :] + zs[k, :].reshape((half, 1)) * (pupdate[k, :, :] - psample[k, js, :])
+                # partner of every updated walker, all temperatures at once
+                js = self._random.randint(0, high=half, size=(self.ntemps, half))
+                partner = np.take_along_axis(psample, js[:, :, None], axis=1)
+                qs = partner + zs[:, :, None] * (pupdate - partner)
                 qslogl, qslogp = self._evaluate(qs)
                 qslogpost = self._tempered_likelihood(qslogl) + qslogp
                 logpaccept = self.dim * np.log(zs) + qslogpost - logpost[:, jupdate::2]
@@ -232,15 +238,17 @@ class Sampler:
             self.nswap_accepted[i] += nacc
             self.nswap_accepted[i - 1] += nacc
             ratios[i - 1] = nacc / self.nwalkers
-            ptemp = np.copy(p[i, iperm[asel], :])
-            logltemp = np.copy(logl[i, iperm[asel]])
-            logprtemp = np.copy(logpost[i, iperm[asel]])
-            p[i, iperm[asel], :] = p[i - 1, i1perm[asel], :]
-            logl[i, iperm[asel]] = logl[i - 1, i1perm[asel]]
-            logpost[i, iperm[asel]] = logpost[i - 1, i1perm[asel]] - dbeta * logl[i - 1, i1perm[asel]]
-            p[i - 1, i1perm[asel], :] = ptemp
-            logl[i - 1, i1perm[asel]] = logltemp
-            logpost[i - 1, i1perm[asel]] = logprtemp + dbeta * logltemp
+            ia, i1a = iperm[asel], i1perm[asel]          # walkers of chain i / chain i-1 that trade places
+            ptemp = p[i, ia, :]
+            logltemp = logl[i, ia]
+            logprtemp = logpost[i, ia]
+            l1 = logl[i - 1, i1a]
+            p[i, ia, :] = p[i - 1, i1a, :]
+            logl[i, ia] = l1
+            logpost[i, ia] = logpost[i - 1, i1a] - dbeta * l1
+            p[i - 1, i1a, :] = ptemp
+            logl[i - 1, i1a] = logltemp
+            logpost[i - 1, i1a] = logprtemp + dbeta * logltemp
         return p, ratios
 
     def _get_ladder_adjustment(self, time, betas0, ratios):
