@@ -424,7 +424,6 @@ def run_c3(args):
     5000-proposal block is latency-bound on one GPU: sharding it does not shorten the step)."""
     import torch
     import nauyaca_b200 as nb
-    from tests.conftest import SpecPS
     world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -434,8 +433,7 @@ def run_c3(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     nb.utils.DEFAULT_DEVICE = local
     spec = dict(load_systems()["doc2"])
-    spec.setdefault("second_term_logL", {"all": spec["second_term_sum"]})
-    PS = SpecPS(spec)
+    PS = nb.SpecSystem(spec)
     nt, nw = 10, 1000
     rng = np.random.mtrand.RandomState(SEED + rank)
     c = cube_of(spec, TRUES_2PL)

@@ -5,11 +5,11 @@ chi-square -> log-likelihood (reference nauyaca/utils.py:16-447), evaluated for 
 batches on the GPU through the C ABI in include/ttvb.h. No CPU fallback.
 """
 from ._lib import (MODE_CUBE, MODE_PHYSICAL, MODE_PHYSICAL_FULL, EVENT_CAP, TTVBError, build)
-from .engine import BatchEngine, system_spec
+from .engine import BatchEngine, SpecSystem, system_spec
 from . import utils
 from .pool import GpuPool, vectorized_chi2
 from .dist import ShardedEvaluator, shard_bounds
-from . import ptsampler, mcmc
+from . import ptsampler, mcmc, optimizers
 
-__all__ = ["BatchEngine", "system_spec", "utils", "GpuPool", "vectorized_chi2", "ShardedEvaluator", "shard_bounds", "ptsampler", "mcmc", "build", "TTVBError", "MODE_CUBE", "MODE_PHYSICAL",
+__all__ = ["BatchEngine", "SpecSystem", "system_spec", "utils", "GpuPool", "vectorized_chi2", "ShardedEvaluator", "shard_bounds", "ptsampler", "mcmc", "optimizers", "build", "TTVBError", "MODE_CUBE", "MODE_PHYSICAL",
            "MODE_PHYSICAL_FULL", "EVENT_CAP"]

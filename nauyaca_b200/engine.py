@@ -38,6 +38,30 @@ def system_spec(PS):
             "second_term_sum": float(sum(PS.second_term_logL.values()))}
 
 
+class SpecSystem:
+    """Attribute container with the PlanetarySystem attributes the hot path reads
+    (planetarysystem.py:184-350), rebuilt from a ``system_spec`` dict. Lets the functions that
+    take a ``PSystem`` (utils.py mirror, GpuPool, make_sampler) run where the reference package
+    is not importable."""
+
+    def __init__(self, spec):
+        from collections import OrderedDict
+        self.system_name = spec.get("system_name", "")
+        self.mstar, self.rstarAU = spec["mstar"], spec["rstarAU"]
+        self.t0, self.ftime, self.dt = spec["t0"], spec["ftime"], spec["dt"]
+        self.npla, self.ndim = spec["npla"], spec["ndim"]
+        self.planets_IDs = dict(spec.get("planets_IDs", {p: o["planet_index"] for p, o in spec["observed"].items()}))
+        self.bounds = [list(b) for b in spec["bounds"]]
+        self.bi, self.bf = list(spec["bi"]), list(spec["bf"])
+        self.hypercube = [list(h) for h in spec["hypercube"]]
+        self.constant_params = OrderedDict((int(k), v) for k, v in
+                                           sorted(spec["constant_params"].items(), key=lambda kv: int(kv[0])))
+        self.transit_times = {p: dict(zip(o["epochs"], o["times"])) for p, o in spec["observed"].items()}
+        self.sigma_obs = {p: dict(zip(o["epochs"], o["sigma"])) for p, o in spec["observed"].items()}
+        self.second_term_logL = dict(spec.get("second_term_logL", {"sum": spec["second_term_sum"]}))
+        self.params_names = spec.get("params_names", "")
+
+
 def _is_torch(x):
     return type(x).__module__.startswith("torch")
 

@@ -1,0 +1,175 @@
+"""The optimizer seam of the reference (optimizers.py:46-203) on the batched GPU path.
+
+``Optimizers.run`` starts ``nsols`` independent DE -> Powell -> Nelder-Mead chains, one
+process each (optimizers.py:185-189); every chain calls ``calculate_chi2`` one vector at a
+time, so the reference evaluates at most ``cores`` vectors concurrently. Here the SAME scipy
+calls (same algorithms, same options as optimizers.py:78-113) run one per Python thread, and
+their objective calls meet in a *rendezvous*: whenever every live chain is waiting for a
+value, all pending vectors are evaluated in ONE ``ttvb_loglike`` batch. A DE generation
+(vectorised scipy objective) contributes 30*ndim vectors per chain, Powell and Nelder-Mead
+one vector per chain and round.
+
+Out of scope: the ``.opt`` result files and the printing of the reference.
+"""
+import threading
+
+import numpy as np
+
+from . import utils as _u
+
+__all__ = ["RendezvousBatcher", "de_pw_nm", "run_optimizers"]
+
+
+class RendezvousBatcher:
+    """Turns many blocking single-caller objectives into few large batches.
+
+    worker threads call ``evaluate(X[m, ndim]) -> f[m]``; ``serve()`` (coordinator thread) waits
+    until every live worker has a request pending, evaluates all of them with one
+    ``batch_fn(X[M, ndim]) -> f[M]`` call and hands the slices back."""
+
+    def __init__(self, batch_fn, nworkers):
+        self.batch_fn = batch_fn
+        self.live = int(nworkers)
+        self.cv = threading.Condition()
+        self.pending = []              # [X, result-holder]
+        self.batches = []              # sizes of the batches served (diagnostics)
+        self.error = None
+
+    def evaluate(self, X):
+        X = np.atleast_2d(np.asarray(X, dtype=np.float64))
+        holder = {"done": False, "f": None}
+        with self.cv:
+            self.pending.append((X, holder))
+            self.cv.notify_all()
+            while not holder["done"]:
+                if self.error is not None:
+                    raise RuntimeError("batch evaluation failed") from self.error
+                self.cv.wait()
+        return holder["f"]
+
+    def worker_done(self):
+        with self.cv:
+            self.live -= 1
+            self.cv.notify_all()
+
+    def serve(self):
+        while True:
+            with self.cv:
+                while self.live > 0 and len(self.pending) < self.live:
+                    self.cv.wait()
+                if self.live <= 0 and not self.pending:
+                    return
+                todo, self.pending = self.pending, []
+            try:
+                sizes = [x.shape[0] for x, _ in todo]
+                f = np.asarray(self.batch_fn(np.concatenate([x for x, _ in todo], axis=0)), dtype=np.float64)
+                self.batches.append(int(sum(sizes)))
+            except BaseException as e:      # wake the workers up, then re-raise here
+                with self.cv:
+                    self.error = e
+                    self.cv.notify_all()
+                raise
+            with self.cv:
+                o = 0
+                for (x, holder), n in zip(todo, sizes):
+                    holder["f"] = f[o:o + n]
+                    holder["done"] = True
+                    o += n
+                self.cv.notify_all()
+
+
+def _chain(PSystem_bounds, ndim, evaluate, seed, de_opts, powell_opts, nm_opts, out, idx, batcher):
+    """One DE -> Powell -> Nelder-Mead chain with the reference's settings (optimizers.py:78-113)."""
+    from scipy.optimize import differential_evolution, minimize
+    try:
+        box = {"lo": np.array([b[0] for b in PSystem_bounds]), "hi": np.array([b[1] for b in PSystem_bounds])}
+
+        def chi2_block(X):
+            # calculate_chi2 (utils.py:244-246): +inf outside the chain's current hypercube
+            X = np.atleast_2d(X)
+            inside = np.all((X >= box["lo"]) & (X <= box["hi"]), axis=1)
+            f = np.full(X.shape[0], np.inf)
+            if inside.any():
+                f[inside] = evaluate(X[inside])
+            return f
+
+        def f_vec(x):                      # scipy vectorised DE: x is (ndim, S)
+            x = np.asarray(x)
+            if x.ndim == 1:
+                return float(chi2_block(x[None, :])[0])
+            return chi2_block(np.ascontiguousarray(x.T))
+
+        def f_one(x):
+            return float(chi2_block(np.asarray(x)[None, :])[0])
+
+        de = differential_evolution(f_vec, list(zip(box["lo"], box["hi"])), seed=seed, vectorized=True,
+                                    updating="deferred", **de_opts)
+        x0, f0 = de.x, de.fun
+        # optimizers.py:90: shrink the hypercube around the DE solution for the local stages
+        box["lo"] = np.maximum(0.0, x0 - 0.3)
+        box["hi"] = np.minimum(1.0, x0 + 0.3)
+        x1, f1 = x0, f0
+        if powell_opts is not None:
+            po = minimize(f_one, list(x0), method="Powell", options=powell_opts)
+            x1, f1 = po.x, po.fun
+        nm = minimize(f_one, list(x1), method="Nelder-Mead", options=nm_opts)
+        out[idx] = (float(f0), float(f1), float(nm.fun), np.asarray(nm.x, dtype=np.float64))
+    except BaseException as e:
+        out[idx] = e
+    finally:
+        batcher.worker_done()
+
+
+def de_pw_nm(PSystem, nsols, seed=None, evaluate=None, powell=True, de_opts=None, powell_opts=None, nm_opts=None):
+    """``nsols`` DE -> Powell -> Nelder-Mead chains in lock-step batches.
+
+    Returns a list of ``[f, x_cube(list), x_phys(list)]`` like ``Optimizers.DE_PW_NM``
+    (optimizers.py:46-139), in chain order, plus the batch-size log as second value.
+    evaluate: X[B, ndim] -> chi2[B] on cube vectors (default: the GPU engine of PSystem with the
+    full unit hypercube; each chain applies its own, shrunken, bounds on the host)."""
+    ndim = PSystem.ndim
+    if evaluate is None:
+        eng = _u.engine_for(PSystem)
+        eng.set_cube_bounds([[0.0, 1.0]] * ndim)
+
+        def evaluate(X):
+            return eng.loglike(np.ascontiguousarray(X), mode=0)[0]
+    de_o = dict(disp=False, popsize=30, maxiter=1, polish=False, mutation=(1.2, 1.7), recombination=0.6)
+    de_o.update(de_opts or {})
+    pw_o = dict(maxiter=12000, maxfev=12000, xtol=0.001, ftol=1, disp=False)
+    pw_o.update(powell_opts or {})
+    nm_o = dict(maxiter=15000, maxfev=15000, xatol=0.0001, fatol=1, disp=False, adaptive=True)
+    nm_o.update(nm_opts or {})
+    batcher = RendezvousBatcher(evaluate, nsols)
+    out = [None] * nsols
+    ss = np.random.SeedSequence(seed)
+    seeds = [int(s.generate_state(1)[0]) for s in ss.spawn(nsols)]
+    threads = [threading.Thread(target=_chain, daemon=True,
+                                args=([list(h) for h in PSystem.hypercube], ndim, batcher.evaluate, seeds[i], de_o,
+                                      pw_o if powell else None, nm_o, out, i, batcher)) for i in range(nsols)]
+    for t in threads:
+        t.start()
+    batcher.serve()
+    for t in threads:
+        t.join()
+    for r in out:
+        if isinstance(r, BaseException):
+            raise r
+    X = np.stack([r[3] for r in out])
+    phys = None
+    try:
+        flat, _ = _u.engine_for(PSystem).cube_to_physical(X)
+        phys = [list(_u._remove_constants(PSystem, row)) for row in flat]
+    except Exception:
+        phys = [None] * nsols
+    results = [[out[i][2], X[i].tolist(), phys[i]] for i in range(nsols)]
+    return results, {"batches": batcher.batches, "stages": [(r[0], r[1], r[2]) for r in out]}
+
+
+def run_optimizers(PSystem, nsols=1, seed=None, **kw):
+    """``Optimizers.run`` seam (optimizers.py:142-203) without the files: dict with 'chi2',
+    'cube', 'physical' ordered by chi2 like ``Optimizers.results``."""
+    res, info = de_pw_nm(PSystem, nsols, seed=seed, **kw)
+    order = np.argsort([r[0] for r in res])
+    return {"chi2": np.array([res[i][0] for i in order]), "cube": np.array([res[i][1] for i in order]),
+            "physical": np.array([res[i][2] for i in order]), "info": info}

@@ -88,27 +88,7 @@ def walkers_near(osys_or_spec, center_cube, n, scale, seed):
     return np.clip(c[None, :] + scale * rng.standard_normal((n, c.size)), 0.0, 1.0)
 
 
-class SpecPS:
-    """Stand-in with the attributes of nauyaca.PlanetarySystem that the hot path reads
-    (planetarysystem.py:184-350), rebuilt from a tests/golden/systems.json entry. The real
-    class lives in /root/reference, which does not exist on the GPU box."""
-
-    def __init__(self, spec):
-        from collections import OrderedDict
-        self.system_name = spec.get("system_name", "")
-        self.mstar, self.rstarAU = spec["mstar"], spec["rstarAU"]
-        self.t0, self.ftime, self.dt = spec["t0"], spec["ftime"], spec["dt"]
-        self.npla, self.ndim = spec["npla"], spec["ndim"]
-        self.planets_IDs = dict(spec["planets_IDs"])
-        self.bounds = [list(b) for b in spec["bounds"]]
-        self.bi, self.bf = list(spec["bi"]), list(spec["bf"])
-        self.hypercube = [list(h) for h in spec["hypercube"]]
-        self.constant_params = OrderedDict((int(k), v) for k, v in
-                                           sorted(spec["constant_params"].items(), key=lambda kv: int(kv[0])))
-        self.transit_times = {p: dict(zip(o["epochs"], o["times"])) for p, o in spec["observed"].items()}
-        self.sigma_obs = {p: dict(zip(o["epochs"], o["sigma"])) for p, o in spec["observed"].items()}
-        self.second_term_logL = dict(spec["second_term_logL"])
-        self.params_names = spec.get("params_names", "")
+from nauyaca_b200.engine import SpecSystem as SpecPS   # stand-in for nauyaca.PlanetarySystem (see its docstring)
 
 
 @pytest.fixture(scope="session")

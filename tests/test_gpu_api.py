@@ -105,3 +105,18 @@ def test_pt_sampler_on_gpu(systems, known, spec_ps, oracle):
     assert np.array_equal(r1[2], ref)
     l0 = osys.loglike(p0[0], mode=0)[1]
     assert np.median(r1[2][0]) > np.median(l0)
+
+
+def test_batched_optimizer_chains_on_gpu(systems, spec_ps, oracle):
+    """optimizers.py:46-139 seam: DE -> Powell -> Nelder-Mead chains in rendezvous batches."""
+    import nauyaca_b200 as nb
+    spec = systems["doc2"]; PS = spec_ps(spec); osys = oracle.OracleSystem(spec)
+    out = nb.optimizers.run_optimizers(PS, nsols=8, seed=7, powell_opts={"maxfev": 300}, nm_opts={"maxfev": 500})
+    assert out["chi2"].shape == (8,) and np.all(np.diff(out["chi2"]) >= 0)
+    # every reported chi2 is the oracle's chi2 of the reported cube vector, bit for bit
+    ref = osys.loglike(out["cube"], mode=0)[0]
+    assert np.array_equal(out["chi2"], ref)
+    st = out["info"]["stages"]
+    assert all(s[2] <= s[1] <= s[0] for s in st)                        # each stage improves
+    assert max(out["info"]["batches"]) == 8 * 30 * spec["ndim"]         # a DE generation of all chains in one launch
+    assert out["physical"].shape == (8, spec["ndim"])

@@ -1,0 +1,94 @@
+"""CPU: the rendezvous batching of the optimizer chains (nauyaca_b200/optimizers.py)."""
+import threading
+
+import numpy as np
+import pytest
+
+from nauyaca_b200.optimizers import RendezvousBatcher, de_pw_nm
+
+
+class _PS:
+    def __init__(self, ndim):
+        self.ndim = ndim
+        self.hypercube = [[0.0, 1.0]] * ndim
+        self.npla = 1
+
+
+def _rosen_like(X):
+    X = np.atleast_2d(X)
+    c = np.linspace(0.3, 0.7, X.shape[1])
+    return 1e4 * np.sum((X - c) ** 2, axis=1) + 50.0 * np.sum((X[:, 1:] - X[:, :-1] ** 2 - c[1:] + c[:-1] ** 2) ** 2, axis=1)
+
+
+def test_rendezvous_batches_all_waiting_workers():
+    calls = []
+
+    def batch(X):
+        calls.append(X.shape[0])
+        return X.sum(axis=1)
+    b = RendezvousBatcher(batch, 5)
+    res = {}
+
+    def work(i):
+        try:
+            for k in range(3 + i):                    # workers finish at different times
+                res[(i, k)] = b.evaluate(np.full((1 + (i % 2), 4), float(i + k)))
+        finally:
+            b.worker_done()
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(5)]
+    [t.start() for t in ts]
+    b.serve()
+    [t.join() for t in ts]
+    assert calls[0] == sum(1 + (i % 2) for i in range(5))          # first round: everyone in one batch
+    assert len(calls) == 7                                            # longest worker needs 7 rounds
+    for (i, k), v in res.items():
+        assert np.all(v == 4.0 * (i + k)) and v.shape == (1 + (i % 2),)
+
+
+def test_rendezvous_propagates_errors():
+    b = RendezvousBatcher(lambda X: 1 / 0, 2)
+    errs = []
+
+    def work():
+        try:
+            b.evaluate(np.zeros((1, 2)))
+        except RuntimeError as e:
+            errs.append(e)
+        finally:
+            b.worker_done()
+    ts = [threading.Thread(target=work) for _ in range(2)]
+    [t.start() for t in ts]
+    with pytest.raises(ZeroDivisionError):
+        b.serve()
+    [t.join() for t in ts]
+    assert len(errs) == 2
+
+
+def test_chains_equal_serial_scipy_and_are_batched():
+    """Same seeds, same objective values -> each chain takes exactly the path the serial scipy
+    calls of optimizers.py:78-113 take; the batches carry one request per live chain."""
+    from scipy.optimize import differential_evolution, minimize
+    PS = _PS(4)
+    nsols = 6
+    res, info = de_pw_nm(PS, nsols, seed=123, evaluate=_rosen_like,
+                         powell_opts={"maxfev": 400}, nm_opts={"maxfev": 600})
+    assert max(info["batches"]) == nsols * 30 * 4                     # a DE generation of every chain at once
+    assert np.median(info["batches"]) >= 2
+    ss = np.random.SeedSequence(123)
+    seeds = [int(s.generate_state(1)[0]) for s in ss.spawn(nsols)]
+    for i in range(nsols):
+        box = {"lo": np.zeros(4), "hi": np.ones(4)}
+
+        def f(x):
+            x = np.asarray(x)
+            X = x[None, :] if x.ndim == 1 else x.T
+            v = np.where(np.all((X >= box["lo"]) & (X <= box["hi"]), axis=1), _rosen_like(X), np.inf)
+            return float(v[0]) if x.ndim == 1 else v
+        de = differential_evolution(f, [(0, 1)] * 4, seed=seeds[i], vectorized=True, updating="deferred", disp=False,
+                                    popsize=30, maxiter=1, polish=False, mutation=(1.2, 1.7), recombination=0.6)
+        box["lo"], box["hi"] = np.maximum(0, de.x - .3), np.minimum(1, de.x + .3)
+        po = minimize(f, list(de.x), method="Powell", options=dict(maxiter=12000, maxfev=400, xtol=0.001, ftol=1, disp=False))
+        nm = minimize(f, list(po.x), method="Nelder-Mead",
+                      options=dict(maxiter=15000, maxfev=600, xatol=0.0001, fatol=1, disp=False, adaptive=True))
+        assert info["stages"][i] == (de.fun, po.fun, nm.fun)
+        assert res[i][0] == nm.fun and res[i][1] == list(nm.x)
