@@ -25,57 +25,68 @@ class RendezvousBatcher:
 
     worker threads call ``evaluate(X[m, ndim]) -> f[m]``; ``serve()`` (coordinator thread) waits
     until every live worker has a request pending, evaluates all of them with one
-    ``batch_fn(X[M, ndim]) -> f[M]`` call and hands the slices back."""
+    ``batch_fn(X[M, ndim]) -> f[M]`` call and hands the slices back. Every worker sleeps on its
+    own Event (no thundering herd on a shared condition variable)."""
 
     def __init__(self, batch_fn, nworkers):
         self.batch_fn = batch_fn
         self.live = int(nworkers)
-        self.cv = threading.Condition()
-        self.pending = []              # [X, result-holder]
-        self.batches = []              # sizes of the batches served (diagnostics)
+        self.lock = threading.Lock()
+        self.ready = threading.Event()     # "every live worker is waiting" or "a worker left"
+        self.pending = []                  # [X, holder]
+        self.batches = []                  # sizes of the batches served (diagnostics)
         self.error = None
+        self._local = threading.local()
 
     def evaluate(self, X):
         X = np.atleast_2d(np.asarray(X, dtype=np.float64))
-        holder = {"done": False, "f": None}
-        with self.cv:
+        ev = getattr(self._local, "ev", None)
+        if ev is None:
+            ev = self._local.ev = threading.Event()
+        ev.clear()
+        holder = {"f": None, "ev": ev}
+        with self.lock:
+            if self.error is not None:
+                raise RuntimeError("batch evaluation failed") from self.error
             self.pending.append((X, holder))
-            self.cv.notify_all()
-            while not holder["done"]:
-                if self.error is not None:
-                    raise RuntimeError("batch evaluation failed") from self.error
-                self.cv.wait()
+            if len(self.pending) >= self.live:
+                self.ready.set()
+        ev.wait()
+        if holder["f"] is None:
+            raise RuntimeError("batch evaluation failed") from self.error
         return holder["f"]
 
     def worker_done(self):
-        with self.cv:
+        with self.lock:
             self.live -= 1
-            self.cv.notify_all()
+            self.ready.set()
 
     def serve(self):
         while True:
-            with self.cv:
-                while self.live > 0 and len(self.pending) < self.live:
-                    self.cv.wait()
+            self.ready.wait()
+            with self.lock:
+                self.ready.clear()
                 if self.live <= 0 and not self.pending:
                     return
+                if len(self.pending) < self.live or not self.pending:
+                    continue
                 todo, self.pending = self.pending, []
             try:
                 sizes = [x.shape[0] for x, _ in todo]
                 f = np.asarray(self.batch_fn(np.concatenate([x for x, _ in todo], axis=0)), dtype=np.float64)
                 self.batches.append(int(sum(sizes)))
             except BaseException as e:      # wake the workers up, then re-raise here
-                with self.cv:
+                with self.lock:
                     self.error = e
-                    self.cv.notify_all()
+                    rest, self.pending = self.pending, []
+                for _, holder in todo + rest:
+                    holder["ev"].set()
                 raise
-            with self.cv:
-                o = 0
-                for (x, holder), n in zip(todo, sizes):
-                    holder["f"] = f[o:o + n]
-                    holder["done"] = True
-                    o += n
-                self.cv.notify_all()
+            o = 0
+            for (x, holder), n in zip(todo, sizes):
+                holder["f"] = f[o:o + n]
+                o += n
+                holder["ev"].set()
 
 
 def _chain(PSystem_bounds, ndim, evaluate, seed, de_opts, powell_opts, nm_opts, out, idx, batcher):
