@@ -396,6 +396,7 @@ def run_gpu(args):
                          "frac": achieved / peak if peak else None,
                          "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
                          "traffic_source": traffic["source"] if traffic else None,
+                         "traffic_note": "above the algorithmic bytes by the context hand-over of time-segmented scheduling (DESIGN.md)",
                          "peak_source": "FP64 FMA-chain microbenchmark in this run (MEASURED_PEAKS.json has no FP64 entry)",
                          "nominal_peak": nominal, "frac_of_nominal": achieved / nominal,
                          "kernel_ms": kms, "flop_per_eval": f_eval,
