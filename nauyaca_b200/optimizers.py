@@ -9,7 +9,9 @@ value, all pending vectors are evaluated in ONE ``ttvb_loglike`` batch. A DE gen
 (vectorised scipy objective) contributes 30*ndim vectors per chain, Powell and Nelder-Mead
 one vector per chain and round.
 
-Out of scope: the ``.opt`` result files and the printing of the reference.
+``write_opt_files`` writes the two result tables in the reference's own text layout
+(optimizers.py:122-136, 160-168; utils.writefile :1222) so that ``MCMC(opt_data=np.genfromtxt(
+'*_cube.opt'))`` and ``init_walkers`` of the reference read them unchanged.
 """
 import threading
 
@@ -17,7 +19,7 @@ import numpy as np
 
 from . import utils as _u
 
-__all__ = ["RendezvousBatcher", "de_pw_nm", "run_optimizers"]
+__all__ = ["RendezvousBatcher", "de_pw_nm", "run_optimizers", "write_opt_files"]
 
 
 class RendezvousBatcher:
@@ -184,3 +186,31 @@ def run_optimizers(PSystem, nsols=1, seed=None, **kw):
     order = np.argsort([r[0] for r in res])
     return {"chi2": np.array([res[i][0] for i in order]), "cube": np.array([res[i][1] for i in order]),
             "physical": np.array([res[i][2] for i in order]), "info": info}
+
+
+def _writefile(path, mode, text, align):
+    """utils.py:1222-1232 writefile(): text.split() formatted with `align`."""
+    with open(path, mode) as fh:
+        fh.write(align % tuple(text.split()))
+
+
+def write_opt_files(PSystem, results, path="./", suffix=""):
+    """Write ``<system_name>_cube<suffix>.opt`` and ``<system_name>_phys<suffix>.opt`` in the layout
+    of the reference: a '#Chi2 <params_names>' header (optimizers.py:160-166), then one line per
+    solution, chi2 followed by the values (optimizers.py:122-136). `results` is the list returned
+    by de_pw_nm or the dict returned by run_optimizers. Returns the two file names."""
+    if isinstance(results, dict):
+        rows = [[c, list(x), list(p)] for c, x, p in zip(results["chi2"], results["cube"], results["physical"])]
+    else:
+        rows = results
+    base_cube = f"{path}{PSystem.system_name}_cube{suffix}.opt"
+    base_phys = f"{path}{PSystem.system_name}_phys{suffix}.opt"
+    header = "#Chi2 " + " ".join(PSystem.params_names.split())
+    for name in (base_cube, base_phys):
+        _writefile(name, "w", header, "%-15s" + " %-11s" * (len(header.split()) - 1) + "\n")
+    for f2, x_cube, x_phys in rows:
+        info = "{} \t {} \n".format(str(f2), "  ".join(str(v) for v in x_cube))
+        _writefile(base_cube, "a", info, "%-30s" + " %-11s" * (len(info.split()) - 1) + "\n")
+        info = " " + str(f2) + " " + "  ".join(str(v) for v in x_phys)
+        _writefile(base_phys, "a", info, "%-30s" + " %-11s" * (len(info.split()) - 1) + "\n")
+    return base_cube, base_phys

@@ -92,3 +92,22 @@ def test_chains_equal_serial_scipy_and_are_batched():
                       options=dict(maxiter=15000, maxfev=600, xatol=0.0001, fatol=1, disp=False, adaptive=True))
         assert info["stages"][i] == (de.fun, po.fun, nm.fun)
         assert res[i][0] == nm.fun and res[i][1] == list(nm.x)
+
+
+def test_opt_files_have_the_reference_layout(tmp_path):
+    """The files must be readable the way the reference reads them (np.genfromtxt, header with
+    '#Chi2 <names>', chi2 first: Examples/miscellany.ipynb cell 7)."""
+    from nauyaca_b200.optimizers import write_opt_files
+
+    class PS:
+        system_name = "SysT"
+        params_names = "mass1  period1  ecc1  mass2"
+    rows = [[12.5, [0.1, 0.2, 0.3, 0.4], [1.0, 5.35, 0.01, 2.0]], [3.25, [0.5, 0.6, 0.7, 0.8], [3.0, 5.36, 0.02, 4.0]]]
+    c, p = write_opt_files(PS, rows, path=str(tmp_path) + "/")
+    assert c.endswith("SysT_cube.opt") and p.endswith("SysT_phys.opt")
+    assert open(c).readline().split() == ["#Chi2", "mass1", "period1", "ecc1", "mass2"]
+    cube = np.genfromtxt(c); phys = np.genfromtxt(p)
+    assert cube.shape == (2, 5) and np.array_equal(cube[:, 0], [12.5, 3.25]) and np.array_equal(cube[1, 1:], [0.5, 0.6, 0.7, 0.8])
+    assert np.array_equal(phys[0, 1:], [1.0, 5.35, 0.01, 2.0])
+    best = list(sorted(cube, key=lambda x: x[0]))[0][1:]          # the notebook's idiom
+    assert list(best) == [0.5, 0.6, 0.7, 0.8]

@@ -53,3 +53,24 @@ def test_reference_ephemeris_golden(ref, known):
     with contextlib.redirect_stdout(io.StringIO()):
         assert U.calculate_chi2_physical(known["G2"]["flat_params"], PS) == 3.6e21
         assert U.log_likelihood_func(known["G2"]["flat_params"], PS, cube=False) == -np.inf   # notebook cell 51
+
+
+def test_opt_writer_matches_reference_writefile(ref, tmp_path):
+    """Byte-for-byte the lines the reference's utils.writefile produces for the same text
+    (optimizers.py:122-136, 160-166)."""
+    U, PSs = ref
+    from nauyaca_b200.optimizers import write_opt_files
+    PS = PSs["doc2"]
+    rows = [[45.09121274544064, list(np.linspace(0.05, 0.95, PS.ndim)), list(np.linspace(1.0, 300.0, PS.ndim))]]
+    c, p = write_opt_files(PS, rows, path=str(tmp_path) + "/")
+    rc, rp = str(tmp_path / "ref_cube.opt"), str(tmp_path / "ref_phys.opt")
+    header = '#Chi2 ' + " ".join([i for i in PS.params_names.split()])
+    for f in (rc, rp):
+        U.writefile(f, "w", header, '%-15s' + ' %-11s' * (len(header.split()) - 1) + '\n')
+    f2, x2_cube, x2_phys = rows[0]
+    info = '{} \t {} \n'.format(str(f2), "  ".join([str(it) for it in x2_cube]))
+    U.writefile(rc, 'a', info, '%-30s' + ' %-11s' * (len(info.split()) - 1) + '\n')
+    info = ' ' + str(f2) + ' ' + "  ".join([str(it) for it in x2_phys])
+    U.writefile(rp, 'a', info, '%-30s' + ' %-11s' * (len(info.split()) - 1) + '\n')
+    assert open(c, "rb").read() == open(rc, "rb").read()
+    assert open(p, "rb").read() == open(rp, "rb").read()
