@@ -439,19 +439,28 @@ def run_c3(args):
     rng = np.random.mtrand.RandomState(SEED + rank)
     c = cube_of(spec, TRUES_2PL)
     p0 = np.clip(c[None, None, :] + 0.01 * rng.normal(size=(nt, nw, spec["ndim"])), 0.0, 1.0)
-    sampler = nb.mcmc.make_sampler(PS, p0, tmax=100.0, random=rng)
     eng = nb.utils.engine_for(PS, device=local)
-    it = sampler.sample(p0, iterations=args.warmup + args.steps, thin=1, storechain=False, adapt=True)
-    for _ in range(args.warmup):
-        next(it)
+    if args.host_sampler:
+        sampler = nb.mcmc.make_sampler(PS, p0, tmax=100.0, random=rng)
+        it = sampler.sample(p0, iterations=args.warmup + args.steps, thin=1, storechain=False, adapt=True)
+        for _ in range(args.warmup):
+            next(it)
+    else:
+        sampler = nb.mcmc.make_device_sampler(PS, p0, tmax=100.0, seed=SEED + rank, device=local)
+        next(sampler.sample(p0, iterations=1, adapt=True, storechain=False))
+        if args.warmup > 1:
+            sampler.advance(args.warmup - 1, adapt=True)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     clocks = ClockSampler(local); clocks.start()
     l0 = eng.launch_count()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        p, logpost, logl = next(it)
+    if args.host_sampler:
+        for _ in range(args.steps):
+            p, logpost, logl = next(it)
+    else:
+        p, logpost, logl = sampler.advance(args.steps, adapt=True)      # returns after the state is back on the host
     torch.cuda.synchronize()
     ms = (time.perf_counter() - t0) * 1e3
     launches = eng.launch_count() - l0
@@ -472,11 +481,14 @@ def run_c3(args):
                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                "config": {"workload": "C3: ptemcee-style PT MCMC, 2-planet system (1228 steps, 60 obs), 10 temperatures x 1000 "
-                                      "walkers, one PT iteration per step (2 x 5000 proposals), independent replica per GPU",
+                                      "walkers, one PT iteration per step (2 x 5000 proposals), independent replica per GPU; sampler moves "
+                                      + ("on the host (numpy)" if args.host_sampler else "on the device (ttvb_pt_*)"),
                           "mean_logl_cold": float(np.mean(logl[0])), "swap_fraction_cold": float(sampler.tswap_acceptance_fraction[0]),
                           "l2": "not flushed: a 5000-proposal block is 0.5 MB and latency-bound"},
-               "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": int(2 * B * spec["ndim"] * 8),
-                       "d2h_bytes_per_step": int(2 * B * 20)},
+               "e2e": {"value": value, "unit": "evals/s",
+                       "h2d_bytes_per_step": int(2 * B * spec["ndim"] * 8) if args.host_sampler else 0,
+                       "d2h_bytes_per_step": int(2 * B * 20) if args.host_sampler
+                       else int(nt * nw * (spec["ndim"] + 3) * 8 / args.steps)},
                "gpu_launches": int(launches), "clocks": clk,
                "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                             "frac": achieved / peak, "traffic": None, "kernel_ms": kms, "flop_per_eval": f_eval,
@@ -495,6 +507,7 @@ def main():
     ap.add_argument("--workload", default="c4", choices=["c2", "c3", "c4", "c5"])
     ap.add_argument("--per-kernel", action="store_true", help="read the kernel time after every step (adds a sync)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--host-sampler", action="store_true", help="c3: sampler moves in numpy on the host instead of on the device")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -151,6 +151,37 @@ int ttvb_launch_count(const ttvb_handle *h, int64_t *count);
  * Used as the measured FP64 roofline denominator (MEASURED_PEAKS.json has no FP64 entry). */
 int ttvb_fp64_peak(ttvb_handle *h, double *tflops, float *ms);
 
+/* ------------------------------------------------------------------------------------------
+ * Parallel-tempering ensemble sampler resident on the device.
+ * Replaces, for the reference's default flat prior (MCMC.logprior == 0.0, mcmc.py:505-509), the
+ * iteration of ptemcee.Sampler.sample() that mcmc.py:195-221 drives: two half-ensemble stretch
+ * moves, temperature swaps and the Vousden ladder adaptation, with the likelihood of every
+ * half-step evaluated by the same kernel as ttvb_loglike. Walkers, log-likelihoods and the
+ * ladder stay on the GPU between iterations.
+ */
+typedef struct ttvb_pt ttvb_pt;
+
+/* betas: [ntemps] host, descending from 1 (ptemcee's ladder). a: stretch scale (mcmc.py:190: 10).
+ * adaptation_lag / adaptation_time: mcmc.py:188-189 (1000, 100). mode: TTVB_MODE_CUBE or
+ * TTVB_MODE_PHYSICAL (walkers without the constants), as mcmc.py:129-137 decides. */
+int ttvb_pt_create(ttvb_handle *h, int32_t ntemps, int32_t nwalkers, const double *betas, double a,
+                   double adaptation_lag, double adaptation_time, uint64_t seed, int mode, ttvb_pt **out);
+int ttvb_pt_destroy(ttvb_pt *pt);
+/* Upload walkers p0[ntemps][nwalkers][ndim] (host) and evaluate their log-likelihoods. */
+int ttvb_pt_set_walkers(ttvb_pt *pt, const double *p0, void *stream);
+/* Run `iterations` PT iterations (asynchronous on `stream`). adapt != 0: adapt the ladder. */
+int ttvb_pt_run(ttvb_pt *pt, int64_t iterations, int adapt, void *stream);
+/* Copy the state to host arrays (any may be NULL); synchronises `stream`.
+ * p[ntemps][nwalkers][ndim], logl[ntemps][nwalkers], betas[ntemps], nprop / nprop_accepted
+ * [ntemps][nwalkers], nswap / nswap_accepted [ntemps] (ptemcee's counters). */
+int ttvb_pt_get(ttvb_pt *pt, double *p, double *logl, double *betas, double *nprop, double *nprop_accepted,
+                double *nswap, double *nswap_accepted, void *stream);
+
+/* Self-test hooks of the sampler's random-number machinery (host code, no GPU needed):
+ * Philox4x32-10 block for a counter/key, and the Feistel pairing permutation of {0..n-1}. */
+int ttvb_selftest_philox(const uint32_t counter[4], const uint32_t key[2], uint32_t out[4]);
+int ttvb_selftest_perm(uint32_t n, uint32_t k0, uint32_t k1, uint32_t *perm_out);
+
 #ifdef __cplusplus
 }
 #endif

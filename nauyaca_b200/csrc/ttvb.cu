@@ -13,6 +13,7 @@
 
 #include "../../include/ttvb.h"
 #include "ttvb_kernels.cuh"
+#include "ttvb_pt.cuh"
 
 
 namespace {
@@ -529,6 +530,137 @@ int ttvb_last_kernel_ms(ttvb_handle* h, float* ms) {
 int ttvb_launch_count(const ttvb_handle* h, int64_t* count) {
     if (!h || !count) return fail(TTVB_E_INVALID, "null argument");
     *count = h->launches;
+    return TTVB_OK;
+}
+
+// ---------------------------------------------------------------- device-resident PT sampler
+}  // extern "C"
+
+struct ttvb_pt {
+    ttvb_handle* h = nullptr;
+    ttvb::PTState S{};
+    int mode = 0;
+    double lag = 1000.0, adapt_time = 100.0;
+    long long time = 0;
+    int hb = 1;
+    double* d_block = nullptr;     // one allocation carved into the arrays of S
+};
+
+extern "C" {
+
+int ttvb_pt_create(ttvb_handle* h, int32_t ntemps, int32_t nwalkers, const double* betas, double a, double lag,
+                   double adapt_time, uint64_t seed, int mode, ttvb_pt** out) {
+    if (!h || !betas || !out) return fail(TTVB_E_INVALID, "null argument");
+    *out = nullptr;
+    if (ntemps < 1 || nwalkers < 2 || (nwalkers & 1)) return fail(TTVB_E_INVALID, "need ntemps >= 1 and an even number of walkers");
+    if (nwalkers < 2 * h->ndim) return fail(TTVB_E_INVALID, "The number of walkers must be greater than 2*dimension");
+    if (mode != TTVB_MODE_CUBE && mode != TTVB_MODE_PHYSICAL) return fail(TTVB_E_INVALID, "mode must be cube or physical");
+    if (!(a > 1.0)) return fail(TTVB_E_INVALID, "stretch scale a must be > 1");
+    CU(cudaSetDevice(h->device));
+    ttvb_pt* pt = new (std::nothrow) ttvb_pt();
+    if (!pt) return fail(TTVB_E_INVALID, "out of host memory");
+    pt->h = h; pt->mode = mode; pt->lag = lag; pt->adapt_time = adapt_time;
+    const size_t nt = ntemps, nw = nwalkers, dim = h->ndim, half = nw / 2;
+    const size_t n_p = nt * nw * dim, n_l = nt * nw, n_q = nt * half * dim, n_h = nt * half;
+    const size_t total = n_p + n_l + nt + n_q + n_h + n_h + 2 * n_l + 2 * nt + nt;
+    if (cudaMalloc(&pt->d_block, total * 8) != cudaSuccess) { delete pt; return fail(TTVB_E_CUDA, "cudaMalloc(PT state) failed"); }
+    cudaMemset(pt->d_block, 0, total * 8);
+    double* c = pt->d_block;
+    ttvb::PTState& S = pt->S;
+    S.ntemps = ntemps; S.nwalkers = nwalkers; S.dim = (int)dim; S.a = a;
+    S.p = c; c += n_p; S.logl = c; c += n_l; S.betas = c; c += nt; S.q = c; c += n_q; S.qlogl = c; c += n_h;
+    S.lnz = c; c += n_h; S.nprop = c; c += n_l; S.nprop_acc = c; c += n_l; S.nswap = c; c += nt; S.nswap_acc = c; c += nt;
+    S.ratios = c; c += nt;
+    S.seed0 = (uint32_t)seed; S.seed1 = (uint32_t)(seed >> 32);
+    int bits = 1;
+    while ((1u << bits) < (unsigned)nwalkers) bits++;
+    pt->hb = (bits + 1) / 2;
+    if (cudaMemcpy(S.betas, betas, nt * 8, cudaMemcpyHostToDevice) != cudaSuccess) { ttvb_pt_destroy(pt); return fail(TTVB_E_CUDA, "upload of the ladder failed"); }
+    *out = pt;
+    return TTVB_OK;
+}
+
+int ttvb_pt_destroy(ttvb_pt* pt) {
+    if (!pt) return TTVB_OK;
+    if (pt->d_block) cudaFree(pt->d_block);
+    delete pt;
+    return TTVB_OK;
+}
+
+int ttvb_pt_set_walkers(ttvb_pt* pt, const double* p0, void* stream) {
+    if (!pt || !p0) return fail(TTVB_E_INVALID, "null argument");
+    ttvb_handle* h = pt->h;
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const ttvb::PTState& S = pt->S;
+    const int64_t B = (int64_t)S.ntemps * S.nwalkers;
+    CU(cudaMemcpyAsync(S.p, p0, (size_t)B * S.dim * 8, cudaMemcpyHostToDevice, st));
+    return run_batch(h, S.p, B, pt->mode, nullptr, S.logl, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr,
+                     nullptr, nullptr, stream);
+}
+
+int ttvb_pt_run(ttvb_pt* pt, int64_t iterations, int adapt, void* stream) {
+    if (!pt) return fail(TTVB_E_INVALID, "null argument");
+    ttvb_handle* h = pt->h;
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const ttvb::PTState& S = pt->S;
+    const int half = S.nwalkers / 2;
+    const int64_t B = (int64_t)S.ntemps * half;
+    const int tb = 128, gb = (int)((B + tb - 1) / tb), gw = (S.nwalkers + tb - 1) / tb;
+    for (int64_t n = 0; n < iterations; n++) {
+        for (int j = 0; j < 2; j++) {
+            ttvb::pt_propose_kernel<<<gb, tb, 0, st>>>(S, pt->time, j);
+            int rc = run_batch(h, S.q, B, pt->mode, nullptr, S.qlogl, nullptr, nullptr, 0, nullptr, nullptr, nullptr,
+                               nullptr, nullptr, nullptr, stream);
+            if (rc != TTVB_OK) return rc;
+            ttvb::pt_accept_kernel<<<gb, tb, 0, st>>>(S, pt->time, j);
+            h->launches += 2;
+        }
+        for (int i = S.ntemps - 1; i >= 1; i--) {
+            ttvb::pt_swap_kernel<<<gw, tb, 0, st>>>(S, pt->time, i, pt->hb);
+            h->launches++;
+        }
+        ttvb::pt_ladder_kernel<<<1, 32, 0, st>>>(S, pt->time, adapt, pt->lag, pt->adapt_time);
+        h->launches++;
+        pt->time++;
+    }
+    CU(cudaGetLastError());
+    return TTVB_OK;
+}
+
+int ttvb_pt_get(ttvb_pt* pt, double* p, double* logl, double* betas, double* nprop, double* nprop_acc, double* nswap,
+                double* nswap_acc, void* stream) {
+    if (!pt) return fail(TTVB_E_INVALID, "null argument");
+    CU(cudaSetDevice(pt->h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const ttvb::PTState& S = pt->S;
+    const size_t nl = (size_t)S.ntemps * S.nwalkers;
+    if (p) CU(cudaMemcpyAsync(p, S.p, nl * S.dim * 8, cudaMemcpyDeviceToHost, st));
+    if (logl) CU(cudaMemcpyAsync(logl, S.logl, nl * 8, cudaMemcpyDeviceToHost, st));
+    if (betas) CU(cudaMemcpyAsync(betas, S.betas, (size_t)S.ntemps * 8, cudaMemcpyDeviceToHost, st));
+    if (nprop) CU(cudaMemcpyAsync(nprop, S.nprop, nl * 8, cudaMemcpyDeviceToHost, st));
+    if (nprop_acc) CU(cudaMemcpyAsync(nprop_acc, S.nprop_acc, nl * 8, cudaMemcpyDeviceToHost, st));
+    if (nswap) CU(cudaMemcpyAsync(nswap, S.nswap, (size_t)S.ntemps * 8, cudaMemcpyDeviceToHost, st));
+    if (nswap_acc) CU(cudaMemcpyAsync(nswap_acc, S.nswap_acc, (size_t)S.ntemps * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return TTVB_OK;
+}
+
+int ttvb_selftest_philox(const uint32_t counter[4], const uint32_t key[2], uint32_t out[4]) {
+    if (!counter || !key || !out) return fail(TTVB_E_INVALID, "null argument");
+    uint32_t o[4];
+    ttvb::Philox::gen(counter[0], counter[1], counter[2], counter[3], key[0], key[1], o);
+    for (int i = 0; i < 4; i++) out[i] = o[i];
+    return TTVB_OK;
+}
+
+int ttvb_selftest_perm(uint32_t n, uint32_t k0, uint32_t k1, uint32_t* perm_out) {
+    if (!perm_out || n < 1) return fail(TTVB_E_INVALID, "bad argument");
+    int bits = 1;
+    while ((1u << bits) < n) bits++;
+    const int hb = (bits + 1) / 2;
+    for (uint32_t w = 0; w < n; w++) perm_out[w] = ttvb::feistel_perm(w, n, hb, k0, k1);
     return TTVB_OK;
 }
 

@@ -10,7 +10,7 @@ import numpy as np
 from . import utils as _u
 from .ptsampler import Sampler
 
-__all__ = ["make_sampler", "pt_sample"]
+__all__ = ["make_sampler", "make_device_sampler", "pt_sample"]
 
 
 def _logprior_zero(x, psystem=None):
@@ -47,6 +47,21 @@ def make_sampler(PSystem, p0, betas=None, tmax=None, logprior=None, evaluate=Non
     # the reference's default prior is identically 0.0 (mcmc.py:505-509): no per-vector calls
     blp = (lambda X: np.zeros(X.shape[0])) if logprior is None else None
     return Sampler(batch_logl=evaluate, batch_logp=blp, **kw)
+
+
+def make_device_sampler(PSystem, p0, betas=None, tmax=None, seed=None, device=None):
+    """The same set-up with every sampler move on the GPU (flat prior only): see
+    ptsampler.DeviceSampler. The per-iteration host work disappears; use ``advance(n)`` to run
+    n iterations between two looks at the state."""
+    from .ptsampler import DeviceSampler
+    p0 = np.asarray(p0, dtype=float)
+    ntemps, nwalkers, ndim = p0.shape
+    if ndim != PSystem.ndim:
+        raise ValueError("p0 has the wrong number of dimensions")
+    p0_norm = bool(((p0 >= 0.0) & (p0 <= 1.0)).all())
+    eng = _u.engine_for(PSystem, device=device)
+    return DeviceSampler(eng, nwalkers, ntemps=ntemps, Tmax=tmax, betas=betas, a=10, adaptation_lag=1000.0,
+                         adaptation_time=100.0, seed=seed, cube=p0_norm)
 
 
 def pt_sample(PSystem, p0, iterations, thin=1, **kw):

@@ -28,7 +28,7 @@ and statistical for the sampler (tests/test_ptsampler.py).
 """
 import numpy as np
 
-__all__ = ["Sampler", "default_beta_ladder", "LikePriorEvaluator"]
+__all__ = ["Sampler", "DeviceSampler", "default_beta_ladder", "LikePriorEvaluator"]
 
 
 def default_beta_ladder(ndim, ntemps=None, Tmax=None):
@@ -368,3 +368,122 @@ def _autocorr_integrated_time(x, axis=0, window=50):
     m = [slice(None)] * f.ndim
     m[axis] = slice(1, window)
     return 1 + 2 * np.sum(f[tuple(m)], axis=axis)
+
+
+class DeviceSampler:
+    """The same sampler with every move on the GPU (ttvb_pt_* in include/ttvb.h).
+
+    Walkers, log-likelihoods and the ladder stay resident on the device; one PT iteration is a
+    stream of small kernels around two likelihood launches, and the host only fetches the
+    state when it is asked for. Restrictions: the reference's default flat prior
+    (MCMC.logprior == 0.0, mcmc.py:505-509) and the TTV likelihood of a BatchEngine. Surface:
+    the part of ptemcee.Sampler that mcmc.py:195-284 touches (sample(), chain, betas,
+    acceptance_fraction, tswap_acceptance_fraction, get_autocorr_time())."""
+
+    def __init__(self, engine, nwalkers, ntemps=None, Tmax=None, betas=None, a=2.0, adaptation_lag=10000,
+                 adaptation_time=100, seed=None, cube=True):
+        import ctypes as C
+        from . import _lib
+        self._C, self._lib = C, _lib
+        self.engine = engine
+        self.dim = engine.ndim
+        self.nwalkers = int(nwalkers)
+        b = default_beta_ladder(self.dim, ntemps=ntemps, Tmax=Tmax) if betas is None else np.array(betas, dtype=float)
+        self._betas = np.ascontiguousarray(b, dtype=np.float64)
+        self.ntemps = len(self._betas)
+        if self.nwalkers % 2 != 0:
+            raise ValueError('The number of walkers must be even.')
+        if self.nwalkers < 2 * self.dim:
+            raise ValueError('The number of walkers must be greater than ``2*dimension``.')
+        if seed is None:
+            seed = int(np.random.SeedSequence().generate_state(2, dtype=np.uint32).view(np.uint64)[0])
+        self._pt = C.c_void_p()
+        _lib.check(_lib.lib().ttvb_pt_create(engine._h, self.ntemps, self.nwalkers, self._betas.ctypes.data, float(a),
+                                             float(adaptation_lag), float(adaptation_time), C.c_uint64(seed),
+                                             _lib.MODE_CUBE if cube else _lib.MODE_PHYSICAL, C.byref(self._pt)))
+        self._time = 0
+        self._started = False
+        self._chain = self._logposterior = self._loglikelihood = self._beta_history = None
+        shape = (self.ntemps, self.nwalkers)
+        self._p = np.empty(shape + (self.dim,)); self._logl = np.empty(shape)
+        self.nprop = np.zeros(shape); self.nprop_accepted = np.zeros(shape)
+        self.nswap = np.zeros(self.ntemps); self.nswap_accepted = np.zeros(self.ntemps)
+
+    def close(self):
+        if getattr(self, "_pt", None) is not None and self._pt.value:
+            self._lib.lib().ttvb_pt_destroy(self._pt)
+            self._pt = self._C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _fetch(self):
+        d = lambda a: a.ctypes.data
+        self._lib.check(self._lib.lib().ttvb_pt_get(self._pt, d(self._p), d(self._logl), d(self._betas), d(self.nprop),
+                                                    d(self.nprop_accepted), d(self.nswap), d(self.nswap_accepted), None))
+        with np.errstate(invalid='ignore'):
+            logpost = self._logl * self._betas[:, None]
+        logpost[np.isnan(logpost)] = -np.inf
+        return self._p.copy(), logpost, self._logl.copy()
+
+    def sample(self, p0=None, iterations=1, thin=1, storechain=True, adapt=False, swap_ratios=False):
+        L = self._lib.lib()
+        if p0 is not None:
+            p0 = np.ascontiguousarray(p0, dtype=np.float64)
+            if p0.shape != (self.ntemps, self.nwalkers, self.dim):
+                raise ValueError('p0 must have shape (ntemps, nwalkers, dim).')
+            self._lib.check(L.ttvb_pt_set_walkers(self._pt, p0.ctypes.data, None))
+            self._started = True
+            p, logpost, logl = self._fetch()
+            if (logl == -np.inf).any():
+                raise ValueError('Attempting to start with samples outside posterior support.')
+        elif not self._started:
+            raise ValueError('Initial walker positions not specified.')
+        if storechain:
+            nsave = iterations // thin
+            z = lambda *s: np.zeros(s)
+            if self._chain is None:
+                isave = 0
+                self._chain = z(self.ntemps, self.nwalkers, nsave, self.dim)
+                self._logposterior = z(self.ntemps, self.nwalkers, nsave); self._loglikelihood = z(self.ntemps, self.nwalkers, nsave)
+                self._beta_history = z(self.ntemps, nsave)
+            else:
+                isave = self._chain.shape[2]
+                self._chain = np.concatenate((self._chain, z(self.ntemps, self.nwalkers, nsave, self.dim)), axis=2)
+                self._logposterior = np.concatenate((self._logposterior, z(self.ntemps, self.nwalkers, nsave)), axis=2)
+                self._loglikelihood = np.concatenate((self._loglikelihood, z(self.ntemps, self.nwalkers, nsave)), axis=2)
+                self._beta_history = np.concatenate((self._beta_history, z(self.ntemps, nsave)), axis=1)
+        for _ in range(iterations):
+            self._lib.check(L.ttvb_pt_run(self._pt, 1, 1 if adapt else 0, None))
+            p, logpost, logl = self._fetch()
+            if (self._time + 1) % thin == 0 and storechain:
+                self._chain[:, :, isave, :] = p
+                self._logposterior[:, :, isave] = logpost
+                self._loglikelihood[:, :, isave] = logl
+                self._beta_history[:, isave] = self._betas
+                isave += 1
+            self._time += 1
+            yield p, logpost, logl
+
+    def advance(self, iterations, adapt=True):
+        """Run `iterations` PT iterations without fetching anything in between (the fast path:
+        nauyaca only looks at the state every `intra_steps` iterations, mcmc.py:227-229)."""
+        if not self._started:
+            raise ValueError('Initial walker positions not specified.')
+        self._lib.check(self._lib.lib().ttvb_pt_run(self._pt, int(iterations), 1 if adapt else 0, None))
+        self._time += int(iterations)
+        return self._fetch()
+
+    run_mcmc = Sampler.run_mcmc
+    betas = property(lambda self: self._betas)
+    time = property(lambda self: self._time)
+    chain = property(lambda self: self._chain)
+    logprobability = property(lambda self: self._logposterior)
+    loglikelihood = property(lambda self: self._loglikelihood)
+    beta_history = property(lambda self: self._beta_history)
+    tswap_acceptance_fraction = property(lambda self: self.nswap_accepted / self.nswap)
+    acceptance_fraction = property(lambda self: self.nprop_accepted / self.nprop)
+    get_autocorr_time = Sampler.get_autocorr_time

@@ -120,3 +120,49 @@ def test_batched_optimizer_chains_on_gpu(systems, spec_ps, oracle):
     assert all(s[2] <= s[1] <= s[0] for s in st)                        # each stage improves
     assert max(out["info"]["batches"]) == 8 * 30 * spec["ndim"]         # a DE generation of all chains in one launch
     assert out["physical"].shape == (8, spec["ndim"])
+
+
+def test_device_sampler(systems, known, spec_ps, oracle):
+    """ttvb_pt_*: the PT iteration on the device. Bookkeeping invariants (every stored logl is
+    the oracle's logl of the stored walker, bit for bit; the ladder keeps its ends and its
+    order; counters add up) and statistical agreement with the host sampler."""
+    import nauyaca_b200 as nb
+    import bench
+    spec = systems["doc2"]; PS = spec_ps(spec); osys = oracle.OracleSystem(spec)
+    c = bench.cube_of(spec, known["G4"]["flat_params"])
+    rng = np.random.mtrand.RandomState(11)
+    nt, nw, dim = 6, 60, spec["ndim"]
+    p0 = np.clip(c[None, None, :] + 0.01 * rng.normal(size=(nt, nw, dim)), 0, 1)
+    dev = nb.mcmc.make_device_sampler(PS, p0, tmax=50.0, seed=1234)
+    n = 0
+    for p, logpost, logl in dev.sample(p0, iterations=40, thin=4, adapt=True):
+        n += 1
+    assert n == 40 and dev.chain.shape == (nt, nw, 10, dim)
+    ref = osys.loglike(p.reshape(-1, dim), mode=0)[1].reshape(nt, nw)
+    assert np.array_equal(logl, ref)                                   # p and logl moved together through accepts and swaps
+    assert np.allclose(logpost, logl * dev.betas[:, None])
+    b = dev.betas
+    assert b[0] == 1.0 and abs(b[-1] - 1 / 50.0) < 1e-15 and np.all(np.diff(b) < 0)
+    assert np.all(dev.nprop == 40) and np.all(dev.nprop_accepted <= 40)
+    assert dev.nswap[0] == 40 * nw and dev.nswap[1] == 80 * nw and np.all(dev.nswap_accepted <= dev.nswap)
+    assert 0.05 < dev.acceptance_fraction[0].mean() < 0.95
+    assert dev.get_autocorr_time().shape == (nt, dim)
+    # same seed -> same chain (counter-based RNG), different seed -> different chain
+    dev2 = nb.mcmc.make_device_sampler(PS, p0, tmax=50.0, seed=1234)
+    r2 = dev2.run_mcmc(p0, iterations=40, adapt=True)
+    assert np.array_equal(r2[0], p)
+    # advance(n) == n single iterations
+    dev3 = nb.mcmc.make_device_sampler(PS, p0, tmax=50.0, seed=1234)
+    next(dev3.sample(p0, iterations=1, adapt=True, storechain=False))
+    r3 = dev3.advance(39, adapt=True)
+    assert np.array_equal(r3[0], p)
+    # statistics against the host sampler after the same number of iterations
+    host = nb.mcmc.make_sampler(PS, p0, tmax=50.0, random=np.random.mtrand.RandomState(5))
+    rh = host.run_mcmc(p0, iterations=150, adapt=True)
+    rd = nb.mcmc.make_device_sampler(PS, p0, tmax=50.0, seed=77)
+    next(rd.sample(p0, iterations=1, adapt=True, storechain=False))
+    pd_, lpd, lld = rd.advance(149, adapt=True)
+    assert abs(np.median(lld[0]) - np.median(rh[2][0])) < 6.0        # cold chains reach the same logl level
+    assert abs(rd.acceptance_fraction[0].mean() - host.acceptance_fraction[0].mean()) < 0.12
+    for s in (dev, dev2, dev3, rd):
+        s.close()
