@@ -170,3 +170,31 @@ def test_full_size_properties(engines, systems):
     # idempotence: a second call gives identical bits
     chi2b, _, _ = eng.loglike(X, mode=0)
     assert np.array_equal(chi2b, chi2)
+
+
+def test_c4_full_size_properties(oracle):
+    """BASELINE config 4 at full size (3 planets, 1500 d, dt 0.1 -> 15001 steps, 10^5 walkers):
+    size-independent properties, plus a sample against the oracle."""
+    import bench
+    import nauyaca_b200 as nb
+    spec, X, _ = bench.make_workload("c4", lambda s: nb.BatchEngine(s))
+    eng = nb.BatchEngine(spec)
+    assert eng.nsteps == 15001 and X.shape == (100_000, 18)
+    chi2, logl, st = eng.loglike(X, mode=0)
+    assert np.all(st == 0) and np.all(np.isfinite(chi2)) and np.all(chi2 > 0)
+    assert np.array_equal(logl, -0.5 * chi2 - spec["second_term_sum"])
+    # the true solution (centre of the walker cloud) reproduces its own ephemeris: chi2 == 0
+    c = bench.cube_of(spec, bench.TRUES_3PL)
+    c0, _, _ = eng.loglike(c[None, :], mode=0)
+    assert c0[0] < 1e-12
+    # position independence across tiles, warps and time segments
+    rng = np.random.default_rng(1)
+    idx = rng.permutation(100_000)[:5000]
+    chi2s, _, _ = eng.loglike(X[idx], mode=0)
+    assert np.array_equal(chi2s, chi2[idx])
+    # a sample against the oracle, bit for bit
+    osys = oracle.OracleSystem(spec)
+    pick = idx[:12]
+    oc, ol, ost = osys.loglike(X[pick], mode=0)
+    assert np.array_equal(oc, chi2[pick]) and np.array_equal(ol, logl[pick])
+    eng.close()
