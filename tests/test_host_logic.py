@@ -124,3 +124,26 @@ def test_vectorized_chi2_shapes(monkeypatch, oracle, systems, spec_ps):
     assert out.shape == (25,)
     assert np.array_equal(out, osys.loglike(np.ascontiguousarray(X.T), mode=0)[0])
     assert f(X[:, 0]) == out[0]
+
+
+def test_sharded_mcmc_gloo(oracle, systems, spec_ps, tmp_path):
+    """The multi-rank MCMC path: replicated sampler state, every likelihood block sharded and
+    all-gathered. Both ranks must hold the chain of the single-process run, and each must have
+    evaluated only half of every block."""
+    import nauyaca_b200 as nb
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    outs = [str(tmp_path / f"m{r}.npz") for r in range(2)]
+    procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "_gloo_mcmc_worker.py"), str(r), "2",
+                               str(port), outs[r]]) for r in range(2)]
+    for p in procs:
+        assert p.wait(timeout=300) == 0
+    spec = systems["doc2"]; PS = spec_ps(spec); osys = oracle.OracleSystem(spec)
+    rng = np.random.mtrand.RandomState(21)
+    p0 = np.clip(0.5 + 0.05 * rng.normal(size=(3, 24, spec["ndim"])), 0, 1)
+    ref = nb.mcmc.make_sampler(PS, p0, tmax=20.0, random=np.random.mtrand.RandomState(4),
+                               evaluate=lambda X: osys.loglike(X, mode=0)[1])
+    p, logpost, logl = ref.run_mcmc(p0, iterations=6, adapt=True)
+    for o in outs:
+        d = np.load(o)
+        assert np.array_equal(d["p"], p) and np.array_equal(d["logl"], logl)
+        assert d["nloc"][0] == 36 and np.all(d["nloc"][1:] == 18)       # 72 initial / 36 per half-step, halved
