@@ -146,3 +146,51 @@ def test_time_segmented_launch_is_bit_identical(oracle, systems, monkeypatch, ns
         assert n[b] == len(e[3])
         _same(tm[b, :n[b]], e[3]); _same(ep[b, :n[b]], e[2])
     eng.close()
+
+
+def test_observed_table_variants(oracle):
+    """Planets without observations, unsorted epoch order in the table, epochs the simulation
+    never reaches (1e20 each, utils.py:199-206), barycentric-Julian-date sized times."""
+    import copy
+    import nauyaca_b200 as nb
+    base = _spec(3, ftime=50.0, dt=0.06)
+    X = np.random.default_rng(8).random((160, base["ndim"]))
+    # (a) middle planet has no TTVs
+    s = copy.deepcopy(base); del s["observed"]["p1"]
+    eng = nb.BatchEngine(s); o = oracle.OracleSystem(s).loglike(X, mode=0)
+    r = eng.loglike(X, mode=0, per_planet=True)
+    _same(r[0], o[0]); _same(r[2], o[2]); assert np.all(r[3][:, 1] == 0.0); eng.close()
+    # (b) epochs far beyond the simulated span: every one costs 1e20
+    s = copy.deepcopy(base); s["observed"]["p0"]["epochs"] = [0, 1, 2, 500, 501, 502]
+    eng = nb.BatchEngine(s); o = oracle.OracleSystem(s).loglike(X, mode=0)
+    r = eng.loglike(X, mode=0); _same(r[0], o[0]); assert np.all(r[0] >= 3e20); eng.close()
+    # (c) table not in epoch order: same set of terms; the sum order may differ in the last bit
+    s = copy.deepcopy(base)
+    for k in ("epochs", "times", "sigma"):
+        s["observed"]["p2"][k] = s["observed"]["p2"][k][::-1]
+    eng = nb.BatchEngine(s); o = oracle.OracleSystem(s).loglike(X, mode=0)
+    r = eng.loglike(X, mode=0)
+    assert np.allclose(r[0], o[0], rtol=1e-14, atol=0); eng.close()
+    # (d) BJD-sized reference time (miscellany.ipynb cell 61: t0 = 2458690)
+    s = copy.deepcopy(base); s["t0"] = 2458690.0; s["ftime"] = 2458740.0
+    for p_ in s["observed"].values():
+        p_["times"] = [t + 2458690.0 for t in p_["times"]]
+    eng = nb.BatchEngine(s); o = oracle.OracleSystem(s).loglike(X, mode=0)
+    r = eng.loglike(X, mode=0); _same(r[0], o[0]); _same(r[2], o[2]); eng.close()
+    # (e) duplicate epochs are refused at creation
+    s = copy.deepcopy(base); s["observed"]["p0"]["epochs"][1] = s["observed"]["p0"]["epochs"][0]
+    with pytest.raises(nb.TTVBError):
+        nb.BatchEngine(s)
+
+
+def test_physical_mode_bounds(oracle):
+    import nauyaca_b200 as nb
+    spec = _spec(2)
+    eng = nb.BatchEngine(spec); osys = oracle.OracleSystem(spec)
+    lo = np.array([b[0] for b in spec["bounds"]]); hi = np.array([b[1] for b in spec["bounds"]])
+    X = lo + np.random.default_rng(3).random((64, spec["ndim"])) * (hi - lo)
+    X[5, 2] = hi[2] + 1e-9; X[6, 0] = lo[0] - 1e-9; X[7] = lo; X[8] = hi
+    r = eng.loglike(X, mode=1); o = osys.loglike(X, mode=1)
+    _same(r[0], o[0]); _same(r[1], o[1]); _same(r[2], o[2])
+    assert r[2][5] & 1 and r[2][6] & 1 and not (r[2][7] & 1) and not (r[2][8] & 1)
+    eng.close()
