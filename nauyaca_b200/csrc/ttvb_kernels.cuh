@@ -125,7 +125,9 @@ __host__ __device__ inline size_t smem_bytes(int N, int nobs, int rowlen) {
 template <int N>
 __device__ __noinline__ void process_batch(const DevSys& S, int count, WarpQ Q, const double* kc_s,
                                            const double* q_s, const double* gm_s, int* res_i,
-                                           double* res_d, int warp_base_tid, long long warp_base_sys) {
+                                           double* res_d, int warp_base_tid, long long warp_base_sys,
+                                           const int* obs_epoch_s, const double* obs_time_s,
+                                           const double* obs_sigma_s) {
     const int lane = threadIdx.x & 31;
     __syncwarp();
     const bool act = lane < count;
@@ -191,38 +193,58 @@ __device__ __noinline__ void process_batch(const DevSys& S, int count, WarpQ Q, 
             }
         }
     }
-    res_i[0 * 32 + lane] = owner;
-    res_i[1 * 32 + lane] = planet;
-    res_i[2 * 32 + lane] = epoch;
-    res_i[3 * 32 + lane] = flags;
-    res_d[0 * 32 + lane] = tt;
-    res_d[1 * 32 + lane] = rs;
+    // ---- this event's chi2 term, computed here by all 32 lanes at once: events with
+    //      rsky > Rstar are not transits (utils.py:113); pos = first observed epoch of the planet
+    //      that is >= the event's epoch (observed epochs before it that the owner has not met
+    //      are missing from the simulation, utils.py:199-206)
+    int info = planet, pos = 0;
+    double term = 0.0;
+    if (act && rs <= S.rstar_au) {
+        info |= 0x100;
+        int a = S.obs_start[planet];
+        const int end = S.obs_start[planet + 1];
+        int b = end;
+        while (a < b) {
+            const int m = (a + b) >> 1;
+            if (obs_epoch_s[m] < epoch) a = m + 1; else b = m;
+        }
+        pos = a;
+        if (pos < end && obs_epoch_s[pos] == epoch) {
+            info |= 0x200;
+            const double d = (obs_time_s[pos] - tt) / obs_sigma_s[pos];
+            term = d * d;
+        }
+    }
+    res_i[0 * 32 + lane] = info;
+    res_i[1 * 32 + lane] = pos;
+    res_i[2 * 32 + lane] = flags;
+    res_i[3 * 32 + lane] = 0;
+    res_d[lane] = term;
+    __syncwarp();
+    // ---- per owner lane, the set of events it owns (queue order = bit order)
+    const unsigned peers = __match_any_sync(0xffffffffu, act ? owner : 32 + lane);
+    if (act && (peers & ((1u << lane) - 1u)) == 0u) res_i[3 * 32 + owner] = (int)peers;
     __syncwarp();
 }
 
-// The owner of each refined event folds it into its chi2 in queue order: observed epochs
-// skipped by the simulation cost 1e20 each (utils.py:199-206), events with rsky > Rstar are
-// not transits (utils.py:113).
-__device__ __forceinline__ void consume_results(const DevSys& S, int cnt, int lane, int tid, const int* res_i,
-                                                const double* res_d, const int* obs_epoch_s,
-                                                const double* obs_time_s, const double* obs_sigma_s,
+// Every lane folds the events it owns into its chi2, in queue order (which keeps the summation
+// order of the reference, utils.py:161-216): observed epochs skipped by the simulation cost
+// 1e20 each (utils.py:199-206), then the event's own term.
+__device__ __forceinline__ void consume_results(int lane, int tid, const int* res_i, const double* res_d,
                                                 double* acc_s, int* cur_s, int& status) {
-#pragma unroll 1
-    for (int j = 0; j < cnt; j++) {
-        if (res_i[0 * 32 + j] == lane) {
-            status |= res_i[3 * 32 + j];
-            const double rsj = res_d[1 * 32 + j];
-            if (rsj <= S.rstar_au) {
-                const int pl = res_i[1 * 32 + j], ep = res_i[2 * 32 + j];
+    unsigned mine = (unsigned)res_i[3 * 32 + lane];
+    while (__any_sync(0xffffffffu, mine != 0u)) {
+        if (mine != 0u) {
+            const int j = __ffs(mine) - 1;
+            mine &= mine - 1u;
+            const int info = res_i[0 * 32 + j];
+            status |= res_i[2 * 32 + j];
+            if (info & 0x100) {
+                const int pl = info & 0xff, pos = res_i[1 * 32 + j];
                 int cur = cur_s[pl * TTVB_TPB + tid];
-                const int end = S.obs_start[pl + 1];
                 double a = acc_s[pl * TTVB_TPB + tid];
-                while (cur < end && obs_epoch_s[cur] < ep) { a += TTVB_PENALTY; cur++; }
-                if (cur < end && obs_epoch_s[cur] == ep) {
-                    const double d = (obs_time_s[cur] - res_d[0 * 32 + j]) / obs_sigma_s[cur];
-                    a += d * d;
-                    cur++;
-                }
+                while (cur < pos) { a += TTVB_PENALTY; cur++; }
+                if ((info & 0x200) && cur == pos) { a += res_d[j]; cur++; }
                 acc_s[pl * TTVB_TPB + tid] = a;
                 cur_s[pl * TTVB_TPB + tid] = cur;
             }
@@ -478,8 +500,8 @@ ttvb_main_kernel(const __grid_constant__ DevSys S) {
                         const int np = __popc(m);
                         qcount += (np < room) ? np : room;
                         if (qcount == 32) {
-                            process_batch<N>(S, 32, Q, kc_s, q_s, gm_s, res_i, res_d, warp_base_tid, warp_base_sys);
-                            consume_results(S, 32, lane, tid, res_i, res_d, obs_epoch_s, obs_time_s, obs_sigma_s, acc_s, cur_s, status);
+                            process_batch<N>(S, 32, Q, kc_s, q_s, gm_s, res_i, res_d, warp_base_tid, warp_base_sys, obs_epoch_s, obs_time_s, obs_sigma_s);
+                            consume_results(lane, tid, res_i, res_d, acc_s, cur_s, status);
                             qcount = 0;
                         }
                         m = __ballot_sync(0xffffffffu, t);
@@ -501,8 +523,8 @@ ttvb_main_kernel(const __grid_constant__ DevSys S) {
         {
             const int cnt = qcount;   // warp-uniform
             if (cnt > 0) {
-                process_batch<N>(S, cnt, Q, kc_s, q_s, gm_s, res_i, res_d, warp_base_tid, warp_base_sys);
-                consume_results(S, cnt, lane, tid, res_i, res_d, obs_epoch_s, obs_time_s, obs_sigma_s, acc_s, cur_s, status);
+                process_batch<N>(S, cnt, Q, kc_s, q_s, gm_s, res_i, res_d, warp_base_tid, warp_base_sys, obs_epoch_s, obs_time_s, obs_sigma_s);
+                consume_results(lane, tid, res_i, res_d, acc_s, cur_s, status);
             }
         }
         if (seg < S.nseg - 1) {
