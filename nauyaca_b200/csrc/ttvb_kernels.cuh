@@ -11,8 +11,8 @@
 // Transit refinement is rare (a few % of steps) and expensive (about three steps' worth
 // of arithmetic). Doing it inline would make every warp pay for it on almost every step
 // with one or two active lanes, so each warp instead owns an EVENT QUEUE (global memory,
-// L2 resident): a lane that triggers pushes its three bracketing states; when 32 events
-// are queued the whole warp refines them together, one event per lane, and the results
+// L2 resident): a lane that triggers pushes its three bracketing states; when 64 events
+// are queued the whole warp refines them together, two events per lane, and the results
 // are handed back to the owning lanes in queue order, which keeps the chi2 summation
 // order of the reference (utils.py:161-216).
 #pragma once
@@ -78,12 +78,15 @@ struct DevSys {
     long long ctx_stride;
 };
 
-// ---- queue layout of one warp: 4x32 ints, then (18N+3)x32 doubles
+// ---- queue layout of one warp: 4 x QCAP ints, then (18N+3) x QCAP doubles (field-major, so that
+//      the refining lanes read coalesced). QCAP = 64: a batch is refined two events per lane in
+//      lockstep (two independent dependency chains per lane).
+#define TTVB_QCAP 64
 template <int N>
 struct QLayout {
     static constexpr int NI = 4;                    // owner, planet, epoch, seq
     static constexpr int ND = 18 * N + 3;           // 3 states x N planets x 6, then T3
-    static constexpr long long BYTES = 32LL * (NI * 4 + ND * 8);
+    static constexpr long long BYTES = (long long)TTVB_QCAP * (NI * 4 + ND * 8);
 };
 
 // per-thread Kepler constants in shared memory: field f of planet i at [(f*N+i)*TPB + tid]
@@ -115,115 +118,176 @@ __host__ __device__ inline size_t smem_bytes(int N, int nobs, int rowlen) {
     b += hist > stage ? hist : stage;                       // history ring / input staging
     b += (size_t)5 * N * TTVB_TPB * 8;                      // gm, kc, q, ieta, s
     b += (size_t)N * TTVB_TPB * 8;                          // chi2 accumulators
-    b += (size_t)(TTVB_TPB / 32) * 32 * 2 * 8;              // result area (doubles)
+    b += (size_t)(TTVB_TPB / 32) * TTVB_QCAP * 8;           // result area (doubles)
     b += (size_t)N * TTVB_TPB * 4;                          // observed-table cursors
-    b += (size_t)(TTVB_TPB / 32) * 32 * 4 * 4;              // result area (ints)
+    b += (size_t)(TTVB_TPB / 32) * TTVB_QCAP * 4 * 4;       // result area (ints)
     return b;
 }
 
-// Refine up to 32 queued events, one per lane, and hand the results to their owners.
+// Refine up to 64 queued events, two per lane IN LOCKSTEP (slots lane and lane+32: two
+// independent dependency chains per lane, which is what hides the FP64 latency here), and
+// hand the results to their owners. Per event the operation sequence is that of the scalar
+// form (kepler_drift / locate_bracket in ttvb_math.cuh), so the bits are the oracle's.
 template <int N>
 __device__ __noinline__ void process_batch(const DevSys& S, int count, WarpQ Q, const double* kc_s,
                                            const double* q_s, const double* gm_s, int* res_i,
                                            double* res_d, int warp_base_tid, long long warp_base_sys,
                                            const int* obs_epoch_s, const double* obs_time_s,
                                            const double* obs_sigma_s) {
+    constexpr int CAP = TTVB_QCAP;
     const int lane = threadIdx.x & 31;
     __syncwarp();
-    const bool act = lane < count;
-    int owner = 0, planet = 0, epoch = 0, seq = 0;
-    double tt = TTVB_BAD_TRANSIT, rs = TTVB_BAD_TRANSIT, vs = TTVB_BAD_TRANSIT;
-    int flags = 0;
-    if (act) {
-        owner = __ldcg(Q.qi + 0 * 32 + lane);
-        planet = __ldcg(Q.qi + 1 * 32 + lane);
-        epoch = __ldcg(Q.qi + 2 * 32 + lane);
-        seq = __ldcg(Q.qi + 3 * 32 + lane);
-        const int otid = warp_base_tid + owner;
-        const double hdt = 0.5 * S.dt;
-        double T3[3];
-        T3[0] = __ldcg(Q.qd + (18 * N + 0) * 32 + lane);
-        T3[1] = __ldcg(Q.qd + (18 * N + 1) * 32 + lane);
-        T3[2] = __ldcg(Q.qd + (18 * N + 2) * 32 + lane);
-        double xs[2][3], vsn[2][3], gs[2];
-        int which[2];
-        which[0] = 1;
-        bool ok = true;
+    bool act[2];
+    int sl[2], owner[2], planet[2], epoch[2], seq[2], otid[2];
+    double T3[2][3];
 #pragma unroll
-        for (int pass = 0; pass < 2; pass++) {
-            const int st = which[pass];
-            const double* base = Q.qd + (long long)st * 6 * N * 32 + lane;
-            double R0 = 0.0, R1 = 0.0, R2 = 0.0, V0 = 0.0, V1 = 0.0, V2 = 0.0;
+    for (int e = 0; e < 2; e++) {
+        const int slot = lane + 32 * e;
+        act[e] = slot < count;
+        sl[e] = act[e] ? slot : (lane < count ? lane : 0);     // idle chains shadow a valid event
+        owner[e] = __ldcg(Q.qi + 0 * CAP + sl[e]);
+        planet[e] = __ldcg(Q.qi + 1 * CAP + sl[e]);
+        epoch[e] = __ldcg(Q.qi + 2 * CAP + sl[e]);
+        seq[e] = __ldcg(Q.qi + 3 * CAP + sl[e]);
+        otid[e] = warp_base_tid + owner[e];
+#pragma unroll
+        for (int k = 0; k < 3; k++) T3[e][k] = __ldcg(Q.qd + (18 * N + k) * CAP + sl[e]);
+    }
+    const double hdt = 0.5 * S.dt;
+    // xs/vsn[e][0]: synchronised astrocentric state of the middle node k; [e][1]: of node k-1
+    // (which == 0) or k+1 (which == 2)
+    double xs[2][2][3] = {}, vsn[2][2][3] = {}, gs[2][2];
+    int which[2] = {1, 1};
+    bool ok[2] = {true, true};
+#pragma unroll
+    for (int pass = 0; pass < 2; pass++) {
+        double R[2][3], V[2][3];
+#pragma unroll
+        for (int e = 0; e < 2; e++)
+#pragma unroll
+            for (int k = 0; k < 3; k++) { R[e][k] = 0.0; V[e][k] = 0.0; }
 #pragma unroll 1
-            for (int j = 0; j <= planet; j++) {
-                double x0 = __ldcg(base + (j * 6 + 0) * 32), x1 = __ldcg(base + (j * 6 + 1) * 32),
-                       x2 = __ldcg(base + (j * 6 + 2) * 32), v0 = __ldcg(base + (j * 6 + 3) * 32),
-                       v1 = __ldcg(base + (j * 6 + 4) * 32), v2 = __ldcg(base + (j * 6 + 5) * 32);
-                ok = kepler_drift(kc_s[j * TTVB_TPB + otid], -hdt, x0, x1, x2, v0, v1, v2) && ok;
-                if (j < planet) {
-                    const double qj = q_s[j * TTVB_TPB + otid];
-                    R0 = fma(qj, x0, R0); R1 = fma(qj, x1, R1); R2 = fma(qj, x2, R2);
-                    V0 = fma(qj, v0, V0); V1 = fma(qj, v1, V1); V2 = fma(qj, v2, V2);
-                } else {
-                    xs[pass][0] = x0 + R0; xs[pass][1] = x1 + R1; xs[pass][2] = x2 + R2;
-                    vsn[pass][0] = v0 + V0; vsn[pass][1] = v1 + V1; vsn[pass][2] = v2 + V2;
+        for (int j = 0; j < N; j++) {
+            const bool on0 = j <= planet[0], on1 = j <= planet[1];
+            if (!__any_sync(0xffffffffu, on0 || on1)) break;
+            State<2> st;
+            MuArray<2> C;
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const double* base = Q.qd + (long long)(which[e] * 6 * N + j * 6) * CAP + sl[e];
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    st.x[e][k] = __ldcg(base + k * CAP);
+                    st.v[e][k] = __ldcg(base + (3 + k) * CAP);
+                }
+                C.m[e] = kc_s[j * TTVB_TPB + otid[e]];
+            }
+            bool conv[2];
+            map_A_joint_t<2, MuArray<2>, false, UniformTau>(C, st, UniformTau{-hdt}, nullptr, nullptr, conv);
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const bool on = j <= planet[e];
+                ok[e] = ok[e] && (conv[e] || !on);
+                const double qj = q_s[j * TTVB_TPB + otid[e]];
+                const bool last = j == planet[e];
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    const double xr = st.x[e][k] + R[e][k], vr = st.v[e][k] + V[e][k];
+                    xs[e][pass][k] = last ? xr : xs[e][pass][k];
+                    vsn[e][pass][k] = last ? vr : vsn[e][pass][k];
+                    const double Rn = fma(qj, st.x[e][k], R[e][k]), Vn = fma(qj, st.v[e][k], V[e][k]);
+                    R[e][k] = (j < planet[e]) ? Rn : R[e][k];
+                    V[e][k] = (j < planet[e]) ? Vn : V[e][k];
                 }
             }
-            gs[pass] = sky_g(xs[pass][0], xs[pass][1], vsn[pass][0], vsn[pass][1]);
-            if (pass == 0) which[1] = (gs[0] > 0.0) ? 0 : 2;
         }
-        if (ok) {
-            const double mu = S.gm0 + gm_s[planet * TTVB_TPB + otid];
-            // pass 0 is node k (mid); pass 1 is node k-1 (which[1]==0) or node k+1
-            if (which[1] == 0)
-                ok = locate_bracket(mu, S.dt, T3[0], T3[1], xs[1], vsn[1], gs[1], xs[0], vsn[0], gs[0], tt, rs, vs);
-            else
-                ok = locate_bracket(mu, S.dt, T3[1], T3[2], xs[0], vsn[0], gs[0], xs[1], vsn[1], gs[1], tt, rs, vs);
-        }
-        if (!ok) {
-            tt = TTVB_BAD_TRANSIT; rs = TTVB_BAD_TRANSIT; vs = TTVB_BAD_TRANSIT;
-            flags = TTVB_ST_BAD_TRANSIT_BIT;
-        }
-        if (S.ev_time != nullptr) {
-            const long long sys = warp_base_sys + owner;
-            if (seq < S.cap) {
-                const long long o = sys * (long long)S.cap + seq;
-                S.ev_planet[o] = planet; S.ev_epoch[o] = epoch;
-                S.ev_time[o] = tt; S.ev_rsky[o] = rs; S.ev_vsky[o] = vs;
-            }
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            gs[e][pass] = sky_g(xs[e][pass][0], xs[e][pass][1], vsn[e][pass][0], vsn[e][pass][1]);
+            if (pass == 0) which[e] = (gs[e][0] > 0.0) ? 0 : 2;
         }
     }
-    // ---- this event's chi2 term, computed here by all 32 lanes at once: events with
+    // ---- the two sides of both brackets: behind sides together, then ahead sides together
+    double mu[2], Tb[2], Ta[2], tau_b[2], tau_a[2], xb[2][3], vb[2][3], xa[2][3], va[2][3];
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+        mu[e] = S.gm0 + gm_s[planet[e] * TTVB_TPB + otid[e]];
+        const bool first = which[e] == 0;     // bracket [T_{k-1}, T_k]; else [T_k, T_{k+1}]
+        const double gb = first ? gs[e][1] : gs[e][0], ga = first ? gs[e][0] : gs[e][1];
+        Tb[e] = first ? T3[e][0] : T3[e][1];
+        Ta[e] = first ? T3[e][1] : T3[e][2];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            xb[e][k] = first ? xs[e][1][k] : xs[e][0][k];
+            vb[e][k] = first ? vsn[e][1][k] : vsn[e][0][k];
+            xa[e][k] = first ? xs[e][0][k] : xs[e][1][k];
+            va[e][k] = first ? vsn[e][0][k] : vsn[e][1][k];
+        }
+        const double den = ga - gb;
+        tau_b[e] = (-gb / den) * S.dt;
+        tau_a[e] = (-ga / den) * S.dt;
+    }
+    double rb[2], vbk[2], ra[2], vak[2];
+    bool okb[2], oka[2];
+    locate_side_joint<2>(mu, xb, vb, tau_b, rb, vbk, okb);
+    locate_side_joint<2>(mu, xa, va, tau_a, ra, vak, oka);
+    // ---- results; this event's chi2 term, computed here by all lanes at once: events with
     //      rsky > Rstar are not transits (utils.py:113); pos = first observed epoch of the planet
     //      that is >= the event's epoch (observed epochs before it that the owner has not met
     //      are missing from the simulation, utils.py:199-206)
-    int info = planet, pos = 0;
-    double term = 0.0;
-    if (act && rs <= S.rstar_au) {
-        info |= 0x100;
-        int a = S.obs_start[planet];
-        const int end = S.obs_start[planet + 1];
-        int b = end;
-        while (a < b) {
-            const int m = (a + b) >> 1;
-            if (obs_epoch_s[m] < epoch) a = m + 1; else b = m;
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+        double tt = TTVB_BAD_TRANSIT, rs = TTVB_BAD_TRANSIT, vs = TTVB_BAD_TRANSIT;
+        int flags = 0;
+        if (ok[e] && okb[e] && oka[e]) {
+            const double tb = Tb[e] + tau_b[e], ta = Ta[e] + tau_a[e];
+            const double wa = tau_b[e] / (tau_b[e] - tau_a[e]);
+            tt = fma(wa, ta - tb, tb);
+            rs = fma(wa, ra[e] - rb[e], rb[e]);
+            vs = fma(wa, vak[e] - vbk[e], vbk[e]);
+        } else {
+            flags = TTVB_ST_BAD_TRANSIT_BIT;
         }
-        pos = a;
-        if (pos < end && obs_epoch_s[pos] == epoch) {
-            info |= 0x200;
-            const double d = (obs_time_s[pos] - tt) / obs_sigma_s[pos];
-            term = d * d;
+        if (act[e] && S.ev_time != nullptr) {
+            const long long sys = warp_base_sys + owner[e];
+            if (seq[e] < S.cap) {
+                const long long o = sys * (long long)S.cap + seq[e];
+                S.ev_planet[o] = planet[e]; S.ev_epoch[o] = epoch[e];
+                S.ev_time[o] = tt; S.ev_rsky[o] = rs; S.ev_vsky[o] = vs;
+            }
         }
+        int info = planet[e], pos = 0;
+        double term = 0.0;
+        if (act[e] && rs <= S.rstar_au) {
+            info |= 0x100;
+            int a = S.obs_start[planet[e]];
+            const int end = S.obs_start[planet[e] + 1];
+            int b = end;
+            while (a < b) {
+                const int m = (a + b) >> 1;
+                if (obs_epoch_s[m] < epoch[e]) a = m + 1; else b = m;
+            }
+            pos = a;
+            if (pos < end && obs_epoch_s[pos] == epoch[e]) {
+                info |= 0x200;
+                const double d = (obs_time_s[pos] - tt) / obs_sigma_s[pos];
+                term = d * d;
+            }
+        }
+        const int slot = lane + 32 * e;
+        res_i[0 * CAP + slot] = info;
+        res_i[1 * CAP + slot] = pos;
+        res_i[2 * CAP + slot] = act[e] ? flags : 0;
+        res_i[3 * CAP + slot] = 0;
+        res_d[slot] = term;
     }
-    res_i[0 * 32 + lane] = info;
-    res_i[1 * 32 + lane] = pos;
-    res_i[2 * 32 + lane] = flags;
-    res_i[3 * 32 + lane] = 0;
-    res_d[lane] = term;
     __syncwarp();
-    // ---- per owner lane, the set of events it owns (queue order = bit order)
-    const unsigned peers = __match_any_sync(0xffffffffu, act ? owner : 32 + lane);
-    if (act && (peers & ((1u << lane) - 1u)) == 0u) res_i[3 * 32 + owner] = (int)peers;
+    // ---- per owner lane, the set of events it owns (queue order = bit order, low word first)
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+        const unsigned peers = __match_any_sync(0xffffffffu, act[e] ? owner[e] : 32 + lane);
+        if (act[e] && (peers & ((1u << lane) - 1u)) == 0u) res_i[3 * CAP + 32 * e + owner[e]] = (int)peers;
+    }
     __syncwarp();
 }
 
@@ -232,25 +296,153 @@ __device__ __noinline__ void process_batch(const DevSys& S, int count, WarpQ Q, 
 // 1e20 each (utils.py:199-206), then the event's own term.
 __device__ __forceinline__ void consume_results(int lane, int tid, const int* res_i, const double* res_d,
                                                 double* acc_s, int* cur_s, int& status) {
-    unsigned mine = (unsigned)res_i[3 * 32 + lane];
-    while (__any_sync(0xffffffffu, mine != 0u)) {
-        if (mine != 0u) {
-            const int j = __ffs(mine) - 1;
-            mine &= mine - 1u;
-            const int info = res_i[0 * 32 + j];
-            status |= res_i[2 * 32 + j];
-            if (info & 0x100) {
-                const int pl = info & 0xff, pos = res_i[1 * 32 + j];
-                int cur = cur_s[pl * TTVB_TPB + tid];
-                double a = acc_s[pl * TTVB_TPB + tid];
-                while (cur < pos) { a += TTVB_PENALTY; cur++; }
-                if ((info & 0x200) && cur == pos) { a += res_d[j]; cur++; }
-                acc_s[pl * TTVB_TPB + tid] = a;
-                cur_s[pl * TTVB_TPB + tid] = cur;
+    constexpr int CAP = TTVB_QCAP;
+#pragma unroll 1
+    for (int e = 0; e < 2; e++) {
+        unsigned mine = (unsigned)res_i[3 * CAP + 32 * e + lane];
+        while (__any_sync(0xffffffffu, mine != 0u)) {
+            if (mine != 0u) {
+                const int j = 32 * e + __ffs(mine) - 1;
+                mine &= mine - 1u;
+                const int info = res_i[0 * CAP + j];
+                status |= res_i[2 * CAP + j];
+                if (info & 0x100) {
+                    const int pl = info & 0xff, pos = res_i[1 * CAP + j];
+                    int cur = cur_s[pl * TTVB_TPB + tid];
+                    double a = acc_s[pl * TTVB_TPB + tid];
+                    while (cur < pos) { a += TTVB_PENALTY; cur++; }
+                    if ((info & 0x200) && cur == pos) { a += res_d[j]; cur++; }
+                    acc_s[pl * TTVB_TPB + tid] = a;
+                    cur_s[pl * TTVB_TPB + tid] = cur;
+                }
             }
         }
     }
     __syncwarp();
+}
+
+// Per-thread state that crosses the boundary of the step loop (lives in local memory while
+// the caller refines a batch of events; in registers inside run_steps).
+template <int N>
+struct StepCtx {
+    State<N> p;
+    double prev_dot[N];
+    double Time, Tm1, Tm2;
+    long long k;              // next step
+    int count[N];             // transit epochs counted so far, per planet
+    int trigmask, nev, status, alive, qcount, pending_push;
+};
+
+// The step loop of one warp: steps cx.k .. k1 (kick, drift, history ring, push of triggered
+// events, trigger check). A LEAF function: no calls inside, so its register allocation does
+// not depend on the event refinement. Returns true when the warp's event queue is full (the
+// caller refines the batch and calls again), false when the steps are done.
+template <int N>
+__device__ __noinline__ bool run_steps(StepCtx<N>& cx, const double dt, const long long nsteps, const long long k1,
+                                       const int o_cst, int* __restrict__ qi, double* __restrict__ qdq) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* const sd = reinterpret_cast<double*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31;
+    double* const hist = sd;
+    SmemConsts<N> C{sd + o_cst + tid};
+    State<N> p = cx.p;
+    double prev_dot[N];
+    int count[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) { prev_dot[i] = cx.prev_dot[i]; count[i] = cx.count[i]; }
+    int trigmask = cx.trigmask, nev = cx.nev, status = cx.status, qcount = cx.qcount;
+    bool alive = cx.alive != 0;
+    bool pending = cx.pending_push != 0;
+    double Time = cx.Time, Tm1 = cx.Tm1, Tm2 = cx.Tm2;
+    long long k = cx.k;
+    bool full = false;
+#pragma unroll 1
+    for (;;) {
+        if (!pending) {
+            if (k > k1) break;
+            if (__ballot_sync(0xffffffffu, alive) == 0u) break;
+            if (alive) {
+                double* hs = hist + (size_t)((k - 1) & 1) * 6 * N * TTVB_TPB + tid;
+#pragma unroll
+                for (int i = 0; i < N; i++)
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        hs[(i * 6 + c) * TTVB_TPB] = p.x[i][c];
+                        hs[(i * 6 + 3 + c) * TTVB_TPB] = p.v[i][c];
+                    }
+                double rj[N], irj[N];
+                map_B<N>(C, p, dt, rj, irj);
+                if (!map_A_after_B<N>(C, p, dt, rj, irj)) { status |= 2; alive = false; trigmask = 0; }
+            }
+            Tm2 = Tm1; Tm1 = Time; Time += dt;
+        }
+        pending = false;
+        // ---- push the events triggered at step k-1 (they now have p_{k-2}, p_{k-1}, p_k)
+        if (__ballot_sync(0xffffffffu, trigmask != 0) != 0u) {
+#pragma unroll 1
+            for (int i = 0; i < N && !full; i++) {
+                bool t = (trigmask >> i) & 1;
+                unsigned m = __ballot_sync(0xffffffffu, t);
+                while (m) {
+                    const int room = TTVB_QCAP - qcount;
+                    const int rank = __popc(m & ((1u << lane) - 1u));
+                    if (t && rank < room) {
+                        const int slot = qcount + rank;
+                        int ci = 0;
+#pragma unroll
+                        for (int j = 0; j < N; j++) if (j == i) { ci = count[j]; count[j] = ci + 1; }
+                        qi[0 * TTVB_QCAP + slot] = lane;
+                        qi[1 * TTVB_QCAP + slot] = i;
+                        qi[2 * TTVB_QCAP + slot] = ci;
+                        qi[3 * TTVB_QCAP + slot] = nev;
+                        nev++;
+                        const double* h0 = hist + (size_t)(k & 1) * 6 * N * TTVB_TPB + tid;        // p_{k-2}
+                        const double* h1 = hist + (size_t)((k - 1) & 1) * 6 * N * TTVB_TPB + tid;  // p_{k-1}
+                        double* qd = qdq + slot;
+#pragma unroll
+                        for (int f = 0; f < 6 * N; f++) {
+                            qd[(0 * 6 * N + f) * TTVB_QCAP] = h0[f * TTVB_TPB];
+                            qd[(1 * 6 * N + f) * TTVB_QCAP] = h1[f * TTVB_TPB];
+                        }
+#pragma unroll
+                        for (int j = 0; j < N; j++)
+#pragma unroll
+                            for (int c = 0; c < 3; c++) {
+                                qd[(2 * 6 * N + j * 6 + c) * TTVB_QCAP] = p.x[j][c];
+                                qd[(2 * 6 * N + j * 6 + 3 + c) * TTVB_QCAP] = p.v[j][c];
+                            }
+                        qd[(18 * N + 0) * TTVB_QCAP] = Tm2;
+                        qd[(18 * N + 1) * TTVB_QCAP] = Tm1;
+                        qd[(18 * N + 2) * TTVB_QCAP] = Time;
+                        t = false;
+                        trigmask &= ~(1 << i);
+                    }
+                    const int np = __popc(m);
+                    qcount += (np < room) ? np : room;
+                    if (qcount == TTVB_QCAP) { full = true; break; }
+                    m = __ballot_sync(0xffffffffu, t);
+                }
+            }
+            if (full) { pending = true; break; }   // come back to the push phase of this step
+        }
+        // ---- trigger check of step k (unsynchronised Jacobi state, as TTVFast)
+        if (alive && k <= nsteps) {
+#pragma unroll
+            for (int i = 0; i < N; i++) {
+                const double cd = sky_g(p.x[i][0], p.x[i][1], p.v[i][0], p.v[i][1]);
+                if (prev_dot[i] < 0.0 && cd > 0.0 && p.x[i][2] > 0.0) trigmask |= (1 << i);
+                prev_dot[i] = cd;
+            }
+        }
+        k++;
+    }
+    cx.p = p;
+#pragma unroll
+    for (int i = 0; i < N; i++) { cx.prev_dot[i] = prev_dot[i]; cx.count[i] = count[i]; }
+    cx.trigmask = trigmask; cx.nev = nev; cx.status = status; cx.alive = alive ? 1 : 0;
+    cx.qcount = qcount; cx.pending_push = pending ? 1 : 0;
+    cx.Time = Time; cx.Tm1 = Tm1; cx.Tm2 = Tm2; cx.k = k;
+    return full;
 }
 
 template <int N>
@@ -267,7 +459,7 @@ ttvb_main_kernel(const __grid_constant__ DevSys S) {
     const int o_cst = ring_d > stage_d ? ring_d : stage_d;
     const int o_acc = o_cst + 5 * N * TTVB_TPB;
     const int o_resd = o_acc + N * TTVB_TPB;
-    const int o_obst = o_resd + (TTVB_TPB / 32) * 32 * 2;
+    const int o_obst = o_resd + (TTVB_TPB / 32) * TTVB_QCAP;
     const int o_obss = o_obst + S.nobs;
     const int o_int = o_obss + S.nobs;                 // in doubles
     double* hist = sd;
@@ -283,21 +475,21 @@ ttvb_main_kernel(const __grid_constant__ DevSys S) {
     int* const si = reinterpret_cast<int*>(smem_raw) + 2 * o_int;
     int* cur_s = si;
     int* res_i_all = si + N * TTVB_TPB;
-    int* obs_epoch_s = res_i_all + (TTVB_TPB / 32) * 32 * 4;
+    int* obs_epoch_s = res_i_all + (TTVB_TPB / 32) * TTVB_QCAP * 4;
 
     for (int i = tid; i < S.nobs; i += TTVB_TPB) {
         obs_time_s[i] = S.obs_time[i];
         obs_sigma_s[i] = S.obs_sigma[i];
         obs_epoch_s[i] = S.obs_epoch[i];
     }
-    int* res_i = res_i_all + warp * 32 * 4;
-    double* res_d = res_d_all + warp * 32 * 2;
+    int* res_i = res_i_all + warp * TTVB_QCAP * 4;
+    double* res_d = res_d_all + warp * TTVB_QCAP;
     WarpQ Q;
     {
         const long long gw = (long long)blockIdx.x * (TTVB_TPB / 32) + warp;
         unsigned char* qb = S.queue + gw * S.queue_stride;
         Q.qi = (int*)qb;
-        Q.qd = (double*)(qb + 32 * QLayout<N>::NI * 4);
+        Q.qd = (double*)(qb + TTVB_QCAP * QLayout<N>::NI * 4);
     }
     const long long ntiles = (S.B + TTVB_TPB - 1) / TTVB_TPB;
     const int rowlen = S.rowlen;
@@ -435,98 +627,37 @@ ttvb_main_kernel(const __grid_constant__ DevSys S) {
         }
         }   // seg == 0
         const bool integrate = (sys < S.B) && !(status & 1);   // out of bounds: chi2=+inf
-        // ---- integration of steps k0..k1 of this unit
+        // ---- integration of steps k0..k1 of this unit: the step loop is a leaf function with its
+        //      own register allocation; it comes back whenever the warp's event queue is full
         const long long k0 = (long long)seg * S.seg_len + 1;
         const long long k1 = (seg == S.nseg - 1) ? (S.nsteps + 1) : (long long)(seg + 1) * S.seg_len;
-        int qcount = 0;
         const int warp_base_tid = warp * 32;
         const long long warp_base_sys = tile_base + warp_base_tid;
-#pragma unroll 1
-        for (long long k = k0; k <= k1; k++) {
-            if (__ballot_sync(0xffffffffu, alive) == 0u) break;
-            if (alive) {
-                double* hs = hist + (size_t)((k - 1) & 1) * 6 * N * TTVB_TPB + tid;
+        StepCtx<N> cx;
+        cx.p = p;
 #pragma unroll
-                for (int i = 0; i < N; i++)
-#pragma unroll
-                    for (int c = 0; c < 3; c++) {
-                        hs[(i * 6 + c) * TTVB_TPB] = p.x[i][c];
-                        hs[(i * 6 + 3 + c) * TTVB_TPB] = p.v[i][c];
-                    }
-                double rj[N], irj[N];
-                map_B<N>(C, p, S.dt, rj, irj);
-                if (!map_A_after_B<N>(C, p, S.dt, rj, irj)) { status |= 2; alive = false; trigmask = 0; }
-            }
-            Tm2 = Tm1; Tm1 = Time; Time += S.dt;
-            // ---- push the events triggered at step k-1 (they now have p_{k-2}, p_{k-1}, p_k)
-            if (__ballot_sync(0xffffffffu, trigmask != 0) != 0u) {
-#pragma unroll 1
-                for (int i = 0; i < N; i++) {
-                    bool t = (trigmask >> i) & 1;
-                    unsigned m = __ballot_sync(0xffffffffu, t);
-                    while (m) {
-                        const int room = 32 - qcount;
-                        const int rank = __popc(m & ((1u << lane) - 1u));
-                        if (t && rank < room) {
-                            const int slot = qcount + rank;
-                            int ci = 0;
-#pragma unroll
-                            for (int j = 0; j < N; j++) if (j == i) { ci = count[j]; count[j] = ci + 1; }
-                            Q.qi[0 * 32 + slot] = lane;
-                            Q.qi[1 * 32 + slot] = i;
-                            Q.qi[2 * 32 + slot] = ci;
-                            Q.qi[3 * 32 + slot] = nev;
-                            nev++;
-                            const double* h0 = hist + (size_t)(k & 1) * 6 * N * TTVB_TPB + tid;        // p_{k-2}
-                            const double* h1 = hist + (size_t)((k - 1) & 1) * 6 * N * TTVB_TPB + tid;  // p_{k-1}
-                            double* qd = Q.qd + slot;
-#pragma unroll
-                            for (int f = 0; f < 6 * N; f++) {
-                                qd[(0 * 6 * N + f) * 32] = h0[f * TTVB_TPB];
-                                qd[(1 * 6 * N + f) * 32] = h1[f * TTVB_TPB];
-                            }
-#pragma unroll
-                            for (int j = 0; j < N; j++)
-#pragma unroll
-                                for (int c = 0; c < 3; c++) {
-                                    qd[(2 * 6 * N + j * 6 + c) * 32] = p.x[j][c];
-                                    qd[(2 * 6 * N + j * 6 + 3 + c) * 32] = p.v[j][c];
-                                }
-                            qd[(18 * N + 0) * 32] = Tm2;
-                            qd[(18 * N + 1) * 32] = Tm1;
-                            qd[(18 * N + 2) * 32] = Time;
-                            t = false;
-                        }
-                        const int np = __popc(m);
-                        qcount += (np < room) ? np : room;
-                        if (qcount == 32) {
-                            process_batch<N>(S, 32, Q, kc_s, q_s, gm_s, res_i, res_d, warp_base_tid, warp_base_sys, obs_epoch_s, obs_time_s, obs_sigma_s);
-                            consume_results(lane, tid, res_i, res_d, acc_s, cur_s, status);
-                            qcount = 0;
-                        }
-                        m = __ballot_sync(0xffffffffu, t);
-                    }
-                }
-                trigmask = 0;
-            }
-            // ---- trigger check of step k (unsynchronised Jacobi state, as TTVFast)
-            if (alive && k <= S.nsteps) {
-#pragma unroll
-                for (int i = 0; i < N; i++) {
-                    const double cd = sky_g(p.x[i][0], p.x[i][1], p.v[i][0], p.v[i][1]);
-                    if (prev_dot[i] < 0.0 && cd > 0.0 && p.x[i][2] > 0.0) trigmask |= (1 << i);
-                    prev_dot[i] = cd;
-                }
-            }
+        for (int i = 0; i < N; i++) { cx.prev_dot[i] = prev_dot[i]; cx.count[i] = count[i]; }
+        cx.trigmask = trigmask; cx.nev = nev; cx.status = status; cx.alive = alive ? 1 : 0;
+        cx.Time = Time; cx.Tm1 = Tm1; cx.Tm2 = Tm2;
+        cx.qcount = 0; cx.k = k0; cx.pending_push = 0;
+        while (run_steps<N>(cx, S.dt, S.nsteps, k1, o_cst, Q.qi, Q.qd)) {
+            process_batch<N>(S, TTVB_QCAP, Q, kc_s, q_s, gm_s, res_i, res_d, warp_base_tid, warp_base_sys, obs_epoch_s, obs_time_s, obs_sigma_s);
+            consume_results(lane, tid, res_i, res_d, acc_s, cur_s, cx.status);
+            cx.qcount = 0;
         }
         // ---- drain the queue
         {
-            const int cnt = qcount;   // warp-uniform
+            const int cnt = cx.qcount;   // warp-uniform
             if (cnt > 0) {
                 process_batch<N>(S, cnt, Q, kc_s, q_s, gm_s, res_i, res_d, warp_base_tid, warp_base_sys, obs_epoch_s, obs_time_s, obs_sigma_s);
-                consume_results(lane, tid, res_i, res_d, acc_s, cur_s, status);
+                consume_results(lane, tid, res_i, res_d, acc_s, cur_s, cx.status);
             }
         }
+        p = cx.p;
+#pragma unroll
+        for (int i = 0; i < N; i++) { prev_dot[i] = cx.prev_dot[i]; count[i] = cx.count[i]; }
+        trigmask = cx.trigmask; nev = cx.nev; status = cx.status; alive = cx.alive != 0;
+        Time = cx.Time; Tm1 = cx.Tm1; Tm2 = cx.Tm2;
         if (seg < S.nseg - 1) {
             // ---- hand the tile over: save the context, publish the segment
             if (sys < S.B) {
