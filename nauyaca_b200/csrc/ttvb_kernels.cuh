@@ -29,6 +29,9 @@
 #define TTVB_MINB 1
 #endif
 #define TTVB_MAX_PLANETS_P1 10
+// row stride (doubles) of the history ring [slot][field][thread]: odd, so that 32 lanes reading
+// 32 different fields of ONE thread (cooperative event push) hit 32 different banks
+#define TTVB_RS (TTVB_TPB + 1)
 #define TTVB_ST_BAD_TRANSIT_BIT 4
 
 namespace ttvb {
@@ -114,7 +117,7 @@ __host__ __device__ inline size_t smem_bytes(int N, int nobs, int rowlen) {
     size_t b = 0;
     b += (size_t)nobs * (8 + 8 + 4);
     b = (b + 7) & ~(size_t)7;
-    size_t hist = (size_t)2 * 6 * N * TTVB_TPB * 8, stage = (size_t)TTVB_TPB * rowlen * 8;
+    size_t hist = (size_t)2 * 6 * N * TTVB_RS * 8, stage = (size_t)TTVB_TPB * rowlen * 8;
     b += hist > stage ? hist : stage;                       // history ring / input staging
     b += (size_t)5 * N * TTVB_TPB * 8;                      // gm, kc, q, ieta, s
     b += (size_t)N * TTVB_TPB * 8;                          // chi2 accumulators
@@ -356,19 +359,20 @@ __device__ __noinline__ bool run_steps(StepCtx<N>& cx, const double dt, const lo
     double Time = cx.Time, Tm1 = cx.Tm1, Tm2 = cx.Tm2;
     long long k = cx.k;
     bool full = false;
+    constexpr int CPR = (12 * N + 31) / 32;
 #pragma unroll 1
     for (;;) {
         if (!pending) {
             if (k > k1) break;
             if (__ballot_sync(0xffffffffu, alive) == 0u) break;
             if (alive) {
-                double* hs = hist + (size_t)((k - 1) & 1) * 6 * N * TTVB_TPB + tid;
+                double* hs = hist + (size_t)((k - 1) & 1) * 6 * N * TTVB_RS + tid;
 #pragma unroll
                 for (int i = 0; i < N; i++)
 #pragma unroll
                     for (int c = 0; c < 3; c++) {
-                        hs[(i * 6 + c) * TTVB_TPB] = p.x[i][c];
-                        hs[(i * 6 + 3 + c) * TTVB_TPB] = p.v[i][c];
+                        hs[(i * 6 + c) * TTVB_RS] = p.x[i][c];
+                        hs[(i * 6 + 3 + c) * TTVB_RS] = p.v[i][c];
                     }
                 double rj[N], irj[N];
                 map_B<N>(C, p, dt, rj, irj);
@@ -377,8 +381,31 @@ __device__ __noinline__ bool run_steps(StepCtx<N>& cx, const double dt, const lo
             Tm2 = Tm1; Tm1 = Time; Time += dt;
         }
         pending = false;
-        // ---- push the events triggered at step k-1 (they now have p_{k-2}, p_{k-1}, p_k)
+        // ---- push the events triggered at step k-1 (they now have p_{k-2}, p_{k-1}, p_k). The two
+        //      older states are in the ring: all 32 lanes copy them together, one field each; the
+        //      owner adds p_k from its registers and the header.
         if (__ballot_sync(0xffffffffu, trigmask != 0) != 0u) {
+            __syncwarp();
+            const int par_old = (int)(k & 1) * 6 * N * TTVB_RS;     // ring slot of p_{k-2}; the other holds p_{k-1}
+            // cooperative copy of the two ring states of one thread (12N doubles): lane handles
+            // element lane + 32 r; element e = s*6N + f is field f of ring state s (0: p_{k-2},
+            // 1: p_{k-1}). Computed here (from a fresh read of the lane id) so that nothing of it
+            // stays live across the arithmetic of the step.
+            int cp_src[CPR], cp_dst[CPR];
+            bool cp_ok[CPR];
+            {
+                unsigned tx;
+                asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tx));
+#pragma unroll
+                for (int r = 0; r < CPR; r++) {
+                    const int e = (int)(tx & 31u) + 32 * r;
+                    cp_ok[r] = e < 12 * N;
+                    const bool nw = e >= 6 * N;
+                    const int f = nw ? e - 6 * N : e;
+                    cp_src[r] = f * TTVB_RS + (nw ? (6 * N * TTVB_RS - par_old) : par_old);
+                    cp_dst[r] = e * TTVB_QCAP;
+                }
+            }
 #pragma unroll 1
             for (int i = 0; i < N && !full; i++) {
                 bool t = (trigmask >> i) & 1;
@@ -386,6 +413,20 @@ __device__ __noinline__ bool run_steps(StepCtx<N>& cx, const double dt, const lo
                 while (m) {
                     const int room = TTVB_QCAP - qcount;
                     const int rank = __popc(m & ((1u << lane) - 1u));
+                    {
+                        unsigned mm = m;
+                        int taken = 0;
+                        while (mm != 0u && taken < room) {
+                            const int b = __ffs(mm) - 1;
+                            mm &= mm - 1u;
+                            const double* src = hist + (tid - lane + b);
+                            double* dst = qdq + (qcount + taken);
+                            taken++;
+#pragma unroll
+                            for (int r = 0; r < CPR; r++)
+                                if (cp_ok[r]) dst[cp_dst[r]] = src[cp_src[r]];
+                        }
+                    }
                     if (t && rank < room) {
                         const int slot = qcount + rank;
                         int ci = 0;
@@ -396,14 +437,7 @@ __device__ __noinline__ bool run_steps(StepCtx<N>& cx, const double dt, const lo
                         qi[2 * TTVB_QCAP + slot] = ci;
                         qi[3 * TTVB_QCAP + slot] = nev;
                         nev++;
-                        const double* h0 = hist + (size_t)(k & 1) * 6 * N * TTVB_TPB + tid;        // p_{k-2}
-                        const double* h1 = hist + (size_t)((k - 1) & 1) * 6 * N * TTVB_TPB + tid;  // p_{k-1}
                         double* qd = qdq + slot;
-#pragma unroll
-                        for (int f = 0; f < 6 * N; f++) {
-                            qd[(0 * 6 * N + f) * TTVB_QCAP] = h0[f * TTVB_TPB];
-                            qd[(1 * 6 * N + f) * TTVB_QCAP] = h1[f * TTVB_TPB];
-                        }
 #pragma unroll
                         for (int j = 0; j < N; j++)
 #pragma unroll
@@ -423,6 +457,7 @@ __device__ __noinline__ bool run_steps(StepCtx<N>& cx, const double dt, const lo
                     m = __ballot_sync(0xffffffffu, t);
                 }
             }
+            __syncwarp();
             if (full) { pending = true; break; }   // come back to the push phase of this step
         }
         // ---- trigger check of step k (unsynchronised Jacobi state, as TTVFast)
@@ -455,7 +490,7 @@ ttvb_main_kernel(const __grid_constant__ DevSys S) {
     // layout: [ring | staging][consts 5N][acc N][res_d][obs_time][obs_sigma] doubles, then
     //         [cur N][res_i][obs_epoch] ints
     double* const sd = reinterpret_cast<double*>(smem_raw);
-    const int ring_d = 2 * 6 * N * TTVB_TPB, stage_d = TTVB_TPB * S.rowlen;
+    const int ring_d = 2 * 6 * N * TTVB_RS, stage_d = TTVB_TPB * S.rowlen;
     const int o_cst = ring_d > stage_d ? ring_d : stage_d;
     const int o_acc = o_cst + 5 * N * TTVB_TPB;
     const int o_resd = o_acc + N * TTVB_TPB;
@@ -535,7 +570,7 @@ ttvb_main_kernel(const __grid_constant__ DevSys S) {
                 for (int i = 0; i < N; i++)
 #pragma unroll
                     for (int c = 0; c < 3; c++) { p.v[i][c] = __ldcg(cd + (f++) * cs); }
-                for (int j = 0; j < 12 * N; j++) hist[(size_t)j * TTVB_TPB + tid] = __ldcg(cd + (f++) * cs);
+                for (int j = 0; j < 12 * N; j++) hist[(size_t)j * TTVB_RS + tid] = __ldcg(cd + (f++) * cs);
 #pragma unroll
                 for (int i = 0; i < N; i++) prev_dot[i] = __ldcg(cd + (f++) * cs);
                 for (int i = 0; i < N; i++) acc_s[i * TTVB_TPB + tid] = __ldcg(cd + (f++) * cs);
@@ -673,7 +708,7 @@ ttvb_main_kernel(const __grid_constant__ DevSys S) {
                 for (int i = 0; i < N; i++)
 #pragma unroll
                     for (int c = 0; c < 3; c++) { cd[(f++) * cs] = p.v[i][c]; }
-                for (int j = 0; j < 12 * N; j++) cd[(f++) * cs] = hist[(size_t)j * TTVB_TPB + tid];
+                for (int j = 0; j < 12 * N; j++) cd[(f++) * cs] = hist[(size_t)j * TTVB_RS + tid];
 #pragma unroll
                 for (int i = 0; i < N; i++) cd[(f++) * cs] = prev_dot[i];
                 for (int i = 0; i < N; i++) cd[(f++) * cs] = acc_s[i * TTVB_TPB + tid];
