@@ -107,6 +107,20 @@ struct SmemConsts {
     }
 };
 
+// Stores into the warp's event queue carry an L2 evict-last policy: the queues are rewritten
+// every few dozen steps and should stay resident in L2 instead of being written back to HBM.
+__device__ __forceinline__ unsigned long long q_policy() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void q_st(double* p, double v, unsigned long long pol) {
+    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void q_st(int* p, int v, unsigned long long pol) {
+    asm volatile("st.global.L2::cache_hint.s32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
+}
+
 struct WarpQ {
     int* qi;
     double* qd;
@@ -386,6 +400,7 @@ __device__ __noinline__ bool run_steps(StepCtx<N>& cx, const double dt, const lo
         //      owner adds p_k from its registers and the header.
         if (__ballot_sync(0xffffffffu, trigmask != 0) != 0u) {
             __syncwarp();
+            const unsigned long long pol = q_policy();
             const int par_old = (int)(k & 1) * 6 * N * TTVB_RS;     // ring slot of p_{k-2}; the other holds p_{k-1}
             // cooperative copy of the two ring states of one thread (12N doubles): lane handles
             // element lane + 32 r; element e = s*6N + f is field f of ring state s (0: p_{k-2},
@@ -424,7 +439,7 @@ __device__ __noinline__ bool run_steps(StepCtx<N>& cx, const double dt, const lo
                             taken++;
 #pragma unroll
                             for (int r = 0; r < CPR; r++)
-                                if (cp_ok[r]) dst[cp_dst[r]] = src[cp_src[r]];
+                                if (cp_ok[r]) q_st(dst + cp_dst[r], src[cp_src[r]], pol);
                         }
                     }
                     if (t && rank < room) {
@@ -432,22 +447,22 @@ __device__ __noinline__ bool run_steps(StepCtx<N>& cx, const double dt, const lo
                         int ci = 0;
 #pragma unroll
                         for (int j = 0; j < N; j++) if (j == i) { ci = count[j]; count[j] = ci + 1; }
-                        qi[0 * TTVB_QCAP + slot] = lane;
-                        qi[1 * TTVB_QCAP + slot] = i;
-                        qi[2 * TTVB_QCAP + slot] = ci;
-                        qi[3 * TTVB_QCAP + slot] = nev;
+                        q_st(qi + 0 * TTVB_QCAP + slot, lane, pol);
+                        q_st(qi + 1 * TTVB_QCAP + slot, i, pol);
+                        q_st(qi + 2 * TTVB_QCAP + slot, ci, pol);
+                        q_st(qi + 3 * TTVB_QCAP + slot, nev, pol);
                         nev++;
                         double* qd = qdq + slot;
 #pragma unroll
                         for (int j = 0; j < N; j++)
 #pragma unroll
                             for (int c = 0; c < 3; c++) {
-                                qd[(2 * 6 * N + j * 6 + c) * TTVB_QCAP] = p.x[j][c];
-                                qd[(2 * 6 * N + j * 6 + 3 + c) * TTVB_QCAP] = p.v[j][c];
+                                q_st(qd + (2 * 6 * N + j * 6 + c) * TTVB_QCAP, p.x[j][c], pol);
+                                q_st(qd + (2 * 6 * N + j * 6 + 3 + c) * TTVB_QCAP, p.v[j][c], pol);
                             }
-                        qd[(18 * N + 0) * TTVB_QCAP] = Tm2;
-                        qd[(18 * N + 1) * TTVB_QCAP] = Tm1;
-                        qd[(18 * N + 2) * TTVB_QCAP] = Time;
+                        q_st(qd + (18 * N + 0) * TTVB_QCAP, Tm2, pol);
+                        q_st(qd + (18 * N + 1) * TTVB_QCAP, Tm1, pol);
+                        q_st(qd + (18 * N + 2) * TTVB_QCAP, Time, pol);
                         t = false;
                         trigmask &= ~(1 << i);
                     }
@@ -703,25 +718,25 @@ ttvb_main_kernel(const __grid_constant__ DevSys S) {
 #pragma unroll
                 for (int i = 0; i < N; i++)
 #pragma unroll
-                    for (int c = 0; c < 3; c++) { cd[(f++) * cs] = p.x[i][c]; }
+                    for (int c = 0; c < 3; c++) { __stcs(cd + (f++) * cs, p.x[i][c]); }
 #pragma unroll
                 for (int i = 0; i < N; i++)
 #pragma unroll
-                    for (int c = 0; c < 3; c++) { cd[(f++) * cs] = p.v[i][c]; }
-                for (int j = 0; j < 12 * N; j++) cd[(f++) * cs] = hist[(size_t)j * TTVB_RS + tid];
+                    for (int c = 0; c < 3; c++) { __stcs(cd + (f++) * cs, p.v[i][c]); }
+                for (int j = 0; j < 12 * N; j++) __stcs(cd + (f++) * cs, hist[(size_t)j * TTVB_RS + tid]);
 #pragma unroll
-                for (int i = 0; i < N; i++) cd[(f++) * cs] = prev_dot[i];
-                for (int i = 0; i < N; i++) cd[(f++) * cs] = acc_s[i * TTVB_TPB + tid];
-                for (int j = 0; j < 5 * N; j++) cd[(f++) * cs] = cst_s[(size_t)j * TTVB_TPB + tid];
-                cd[(f++) * cs] = Time; cd[(f++) * cs] = Tm1; cd[(f++) * cs] = Tm2;
+                for (int i = 0; i < N; i++) __stcs(cd + (f++) * cs, prev_dot[i]);
+                for (int i = 0; i < N; i++) __stcs(cd + (f++) * cs, acc_s[i * TTVB_TPB + tid]);
+                for (int j = 0; j < 5 * N; j++) __stcs(cd + (f++) * cs, cst_s[(size_t)j * TTVB_TPB + tid]);
+                __stcs(cd + (f++) * cs, Time); __stcs(cd + (f++) * cs, Tm1); __stcs(cd + (f++) * cs, Tm2);
                 int g = 0;
 #pragma unroll
-                for (int i = 0; i < N; i++) ci[(g++) * cs] = count[i];
-                for (int i = 0; i < N; i++) ci[(g++) * cs] = cur_s[i * TTVB_TPB + tid];
-                ci[(g++) * cs] = trigmask;
-                ci[(g++) * cs] = nev;
-                ci[(g++) * cs] = status;
-                ci[(g++) * cs] = alive ? 1 : 0;
+                for (int i = 0; i < N; i++) __stcs(ci + (g++) * cs, count[i]);
+                for (int i = 0; i < N; i++) __stcs(ci + (g++) * cs, cur_s[i * TTVB_TPB + tid]);
+                __stcs(ci + (g++) * cs, trigmask);
+                __stcs(ci + (g++) * cs, nev);
+                __stcs(ci + (g++) * cs, status);
+                __stcs(ci + (g++) * cs, alive ? 1 : 0);
             }
             __threadfence();
             __syncthreads();

@@ -110,6 +110,36 @@ def test_identical_walkers_fill_the_queue(oracle):
     eng.close()
 
 
+def test_queue_fills_in_the_middle_of_a_push(oracle):
+    """Warps of 27-31 identical systems plus a few different ones: the 64-slot queue fills while
+    a round of simultaneous triggers is being pushed, so the step loop hands the batch over and
+    resumes the push (and the last batch of every warp is a partial one with an odd count).
+    chi2, status and the event table stay the oracle's, bit for bit."""
+    import nauyaca_b200 as nb
+    spec = _spec(3, ftime=80.0)
+    eng = nb.BatchEngine(spec); osys = oracle.OracleSystem(spec)
+    rng = np.random.default_rng(7)
+    base = rng.random((4, spec["ndim"]))
+    rows = []
+    for w in range(8):                       # 8 warps: 32 - n_other copies of one system, n_other others
+        n_other = 1 + w % 5
+        rows += [base[w % 4]] * (32 - n_other) + [rng.random(spec["ndim"]) for _ in range(n_other)]
+    X = np.array(rows)
+    chi2, logl, st = eng.loglike(X, mode=0)
+    o = osys.loglike(X, mode=0)
+    _same(chi2, o[0]); _same(logl, o[1]); _same(st, o[2])
+    flat, inside = eng.cube_to_physical(X)
+    cap = 256
+    n, pl, ep, tm, rs, vs, st2 = eng.ephemeris(flat, mode=2, cap=cap)
+    for b in range(0, X.shape[0], 3):
+        ost, opl, oep, otm, ors, ovs = oracle.ephemeris(flat[b], spec["mstar"], spec["t0"], spec["dt"], spec["ftime"],
+                                                        cap=cap)
+        k = n[b]
+        assert st2[b] == ost and k == len(otm)
+        _same(pl[b, :k], opl); _same(ep[b, :k], oep); _same(tm[b, :k], otm); _same(rs[b, :k], ors); _same(vs[b, :k], ovs)
+    eng.close()
+
+
 def test_chunked_host_batches(oracle):
     """More rows than the 2^20 staging chunk: host-pointer path loops over chunks."""
     import nauyaca_b200 as nb
