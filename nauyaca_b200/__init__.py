@@ -9,7 +9,8 @@ from .engine import BatchEngine, SpecSystem, system_spec
 from . import utils
 from .pool import GpuPool, vectorized_chi2
 from .dist import ShardedEvaluator, shard_bounds
-from . import ptsampler, mcmc, optimizers
+from . import ptsampler, mcmc, optimizers, walkers
+from .walkers import init_walkers
 
-__all__ = ["BatchEngine", "SpecSystem", "system_spec", "utils", "GpuPool", "vectorized_chi2", "ShardedEvaluator", "shard_bounds", "ptsampler", "mcmc", "optimizers", "build", "TTVBError", "MODE_CUBE", "MODE_PHYSICAL",
+__all__ = ["BatchEngine", "SpecSystem", "system_spec", "utils", "GpuPool", "vectorized_chi2", "ShardedEvaluator", "shard_bounds", "ptsampler", "mcmc", "optimizers", "walkers", "init_walkers", "build", "TTVBError", "MODE_CUBE", "MODE_PHYSICAL",
            "MODE_PHYSICAL_FULL", "EVENT_CAP"]

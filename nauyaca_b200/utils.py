@@ -18,6 +18,7 @@ cube_to_physical       utils.py:403    cube_to_physical
 _insert_constants      utils.py:440    _insert_constants
 _remove_constants      utils.py:450    _remove_constants
 intervals              utils.py:1193   intervals
+init_walkers           utils.py:463    init_walkers (walkers.py)
 """
 import sys
 
@@ -25,11 +26,12 @@ import numpy as np
 
 from ._lib import MODE_CUBE, MODE_PHYSICAL, MODE_PHYSICAL_FULL, EVENT_CAP
 from .engine import BatchEngine, system_spec
+from .walkers import init_walkers  # noqa: F401  (reference keeps it in utils)
 
 __all__ = ['run_TTVFast', 'calculate_ephemeris', 'log_likelihood_func', 'cube_to_physical',
            '_ephemeris', '_remove_constants', '_insert_constants', 'calculate_chi2',
            'calculate_chi2_physical', 'intervals', 'calculate_chi2_batch', 'log_likelihood_batch',
-           'engine_for', 'clear_engine_cache']
+           'engine_for', 'clear_engine_cache', 'init_walkers']
 
 Mearth_to_Msun = 3.0034893488507934e-06     # reference constants.py:65
 
