@@ -436,7 +436,8 @@ def run_c3(args):
     spec = dict(load_systems()["doc2"])
     PS = nb.SpecSystem(spec)
     nt, nw = 10, 1000
-    rng = np.random.mtrand.RandomState(SEED + rank)
+    shard = bool(args.shard_walkers) and world > 1 and not args.host_sampler
+    rng = np.random.mtrand.RandomState(SEED + (0 if shard else rank))
     c = cube_of(spec, TRUES_2PL)
     p0 = np.clip(c[None, None, :] + 0.01 * rng.normal(size=(nt, nw, spec["ndim"])), 0.0, 1.0)
     eng = nb.utils.engine_for(PS, device=local)
@@ -446,7 +447,8 @@ def run_c3(args):
         for _ in range(args.warmup):
             next(it)
     else:
-        sampler = nb.mcmc.make_device_sampler(PS, p0, tmax=100.0, seed=SEED + rank, device=local)
+        sampler = nb.mcmc.make_device_sampler(PS, p0, tmax=100.0, seed=SEED + (0 if shard else rank), device=local,
+                                              shard=shard)
         next(sampler.sample(p0, iterations=1, adapt=True, storechain=False))
         if args.warmup > 1:
             sampler.advance(args.warmup - 1, adapt=True)
@@ -470,7 +472,7 @@ def run_c3(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
-    evals = world * args.steps * nt * nw
+    evals = (1 if shard else world) * args.steps * nt * nw
     if rank == 0:
         B = nt * nw // 2
         f_eval = flops_per_eval(spec["npla"], eng.nsteps, 60.0)
@@ -479,9 +481,11 @@ def run_c3(args):
         achieved = f_eval * B / (kms * 1e-3) / 1e12
         out = {"metric": "likelihood evals/sec", "value": value, "unit": "evals/s", "n_gpus": world,
                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-               "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "scaling": "strong" if shard else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                "config": {"workload": "C3: ptemcee-style PT MCMC, 2-planet system (1228 steps, 60 obs), 10 temperatures x 1000 "
-                                      "walkers, one PT iteration per step (2 x 5000 proposals), independent replica per GPU; sampler moves "
+                                      "walkers, one PT iteration per step (2 x 5000 proposals), "
+                                      + ("ONE ensemble, proposals sharded over the GPUs, all_gather(logl) per half-step"
+                                         if shard else "independent replica per GPU") + "; sampler moves "
                                       + ("on the host (numpy)" if args.host_sampler else "on the device (ttvb_pt_*)"),
                           "mean_logl_cold": float(np.mean(logl[0])), "swap_fraction_cold": float(sampler.tswap_acceptance_fraction[0]),
                           "l2": "not flushed: a 5000-proposal block is 0.5 MB and latency-bound"},
@@ -508,6 +512,9 @@ def main():
     ap.add_argument("--per-kernel", action="store_true", help="read the kernel time after every step (adds a sync)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--host-sampler", action="store_true", help="c3: sampler moves in numpy on the host instead of on the device")
+    ap.add_argument("--shard-walkers", action="store_true",
+                    help="c3 with N > 1: ONE ensemble, the proposals of every half-step sharded over the GPUs and their "
+                         "log-likelihoods all-gathered over NCCL (strong scaling) instead of one replica per GPU")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

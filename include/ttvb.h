@@ -171,6 +171,16 @@ int ttvb_pt_destroy(ttvb_pt *pt);
 int ttvb_pt_set_walkers(ttvb_pt *pt, const double *p0, void *stream);
 /* Run `iterations` PT iterations (asynchronous on `stream`). adapt != 0: adapt the ladder. */
 int ttvb_pt_run(ttvb_pt *pt, int64_t iterations, int adapt, void *stream);
+/* The same iteration in pieces, for ensembles whose likelihood evaluations are sharded over
+ * several GPUs: every rank holds the whole ensemble (same seed, same p0; the
+ * moves are deterministic functions of seed and iteration), evaluates the proposals [lo, hi)
+ * of the half-step's block of ntemps*nwalkers/2, the caller all-gathers the block of proposal
+ * log-likelihoods (ttvb_pt_proposal_logl: device pointer, length, and the capacity available
+ * for a padded in-place gather) over NCCL, and every rank accepts / swaps / adapts alike.
+ * One iteration = begin(0) gather end(0) begin(1) gather end(1). */
+int ttvb_pt_half_begin(ttvb_pt *pt, int half, int64_t lo, int64_t hi, void *stream);
+int ttvb_pt_half_end(ttvb_pt *pt, int half, int adapt, void *stream);
+int ttvb_pt_proposal_logl(ttvb_pt *pt, double **dev_ptr, int64_t *n, int64_t *capacity);
 /* Copy the state to host arrays (any may be NULL); synchronises `stream`.
  * p[ntemps][nwalkers][ndim], logl[ntemps][nwalkers], betas[ntemps], nprop / nprop_accepted
  * [ntemps][nwalkers], nswap / nswap_accepted [ntemps] (ptemcee's counters). */

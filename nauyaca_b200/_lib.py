@@ -13,6 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TTVB_LIB") or os.path.join(_HERE, "libttvb.so")   # TTVB_LIB: kernel experiments
 SRC = os.path.join(_HERE, "csrc", "ttvb.cu")
 DEPS = [SRC, os.path.join(_HERE, "csrc", "ttvb_kernels.cuh"), os.path.join(_HERE, "csrc", "ttvb_math.cuh"),
+        os.path.join(_HERE, "csrc", "ttvb_pt.cuh"),
         os.path.join(os.path.dirname(_HERE), "include", "ttvb.h")]
 
 # -fmad=false: only the fma() calls written in the source are fused, so the device
@@ -29,7 +30,7 @@ MAX_PLANETS = 9
 EXPORTS = ["ttvb_last_error", "ttvb_version", "ttvb_device_count", "ttvb_create", "ttvb_destroy",
            "ttvb_set_cube_bounds", "ttvb_nsteps", "ttvb_loglike", "ttvb_ephemeris", "ttvb_cube_to_physical",
            "ttvb_last_kernel_ms", "ttvb_launch_count", "ttvb_fp64_peak",
-           "ttvb_pt_create", "ttvb_pt_destroy", "ttvb_pt_set_walkers", "ttvb_pt_run", "ttvb_pt_get",
+           "ttvb_pt_create", "ttvb_pt_destroy", "ttvb_pt_set_walkers", "ttvb_pt_run", "ttvb_pt_get", "ttvb_pt_half_begin", "ttvb_pt_half_end", "ttvb_pt_proposal_logl",
            "ttvb_selftest_philox", "ttvb_selftest_perm"]
 
 
@@ -97,6 +98,9 @@ def lib():
     L.ttvb_pt_set_walkers.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.ttvb_pt_run.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p]
     L.ttvb_pt_get.argtypes = [C.c_void_p] + [C.c_void_p] * 8
+    L.ttvb_pt_half_begin.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p]
+    L.ttvb_pt_half_end.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    L.ttvb_pt_proposal_logl.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.ttvb_fp64_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_float)]
     _lib = L
     return L

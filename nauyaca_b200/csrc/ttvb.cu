@@ -562,13 +562,14 @@ int ttvb_pt_create(ttvb_handle* h, int32_t ntemps, int32_t nwalkers, const doubl
     pt->h = h; pt->mode = mode; pt->lag = lag; pt->adapt_time = adapt_time;
     const size_t nt = ntemps, nw = nwalkers, dim = h->ndim, half = nw / 2;
     const size_t n_p = nt * nw * dim, n_l = nt * nw, n_q = nt * half * dim, n_h = nt * half;
-    const size_t total = n_p + n_l + nt + n_q + n_h + n_h + 2 * n_l + 2 * nt + nt;
+    const size_t pad = 64;         // room behind qlogl for the padded all-gather of sharded runs
+    const size_t total = n_p + n_l + nt + n_q + n_h + pad + n_h + 2 * n_l + 2 * nt + nt;
     if (cudaMalloc(&pt->d_block, total * 8) != cudaSuccess) { delete pt; return fail(TTVB_E_CUDA, "cudaMalloc(PT state) failed"); }
     cudaMemset(pt->d_block, 0, total * 8);
     double* c = pt->d_block;
     ttvb::PTState& S = pt->S;
     S.ntemps = ntemps; S.nwalkers = nwalkers; S.dim = (int)dim; S.a = a;
-    S.p = c; c += n_p; S.logl = c; c += n_l; S.betas = c; c += nt; S.q = c; c += n_q; S.qlogl = c; c += n_h;
+    S.p = c; c += n_p; S.logl = c; c += n_l; S.betas = c; c += nt; S.q = c; c += n_q; S.qlogl = c; c += n_h + pad;
     S.lnz = c; c += n_h; S.nprop = c; c += n_l; S.nprop_acc = c; c += n_l; S.nswap = c; c += nt; S.nswap_acc = c; c += nt;
     S.ratios = c; c += nt;
     S.seed0 = (uint32_t)seed; S.seed1 = (uint32_t)(seed >> 32);
@@ -626,6 +627,59 @@ int ttvb_pt_run(ttvb_pt* pt, int64_t iterations, int adapt, void* stream) {
         pt->time++;
     }
     CU(cudaGetLastError());
+    return TTVB_OK;
+}
+
+// ---- one PT iteration in pieces, for runs where the proposals of a half-step are sharded
+//      over several GPUs (every rank holds the whole ensemble and makes the same moves)
+int ttvb_pt_half_begin(ttvb_pt* pt, int half, int64_t lo, int64_t hi, void* stream) {
+    if (!pt) return fail(TTVB_E_INVALID, "null argument");
+    ttvb_handle* h = pt->h;
+    const ttvb::PTState& S = pt->S;
+    const int64_t B = (int64_t)S.ntemps * (S.nwalkers / 2);
+    if (half < 0 || half > 1 || lo < 0 || hi > B || lo > hi) return fail(TTVB_E_INVALID, "bad half or proposal range");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int tb = 128, gb = (int)((B + tb - 1) / tb);
+    ttvb::pt_propose_kernel<<<gb, tb, 0, st>>>(S, pt->time, half);
+    h->launches++;
+    CU(cudaGetLastError());
+    if (hi == lo) return TTVB_OK;
+    return run_batch(h, S.q + lo * S.dim, hi - lo, pt->mode, nullptr, S.qlogl + lo, nullptr, nullptr, 0, nullptr,
+                     nullptr, nullptr, nullptr, nullptr, nullptr, stream);
+}
+
+int ttvb_pt_half_end(ttvb_pt* pt, int half, int adapt, void* stream) {
+    if (!pt) return fail(TTVB_E_INVALID, "null argument");
+    if (half < 0 || half > 1) return fail(TTVB_E_INVALID, "bad half");
+    ttvb_handle* h = pt->h;
+    CU(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const ttvb::PTState& S = pt->S;
+    const int64_t B = (int64_t)S.ntemps * (S.nwalkers / 2);
+    const int tb = 128, gb = (int)((B + tb - 1) / tb), gw = (S.nwalkers + tb - 1) / tb;
+    ttvb::pt_accept_kernel<<<gb, tb, 0, st>>>(S, pt->time, half);
+    h->launches++;
+    if (half == 1) {
+        for (int i = S.ntemps - 1; i >= 1; i--) {
+            ttvb::pt_swap_kernel<<<gw, tb, 0, st>>>(S, pt->time, i, pt->hb);
+            h->launches++;
+        }
+        ttvb::pt_ladder_kernel<<<1, 32, 0, st>>>(S, pt->time, adapt, pt->lag, pt->adapt_time);
+        h->launches++;
+        pt->time++;
+    }
+    CU(cudaGetLastError());
+    return TTVB_OK;
+}
+
+int ttvb_pt_proposal_logl(ttvb_pt* pt, double** dev_ptr, int64_t* n, int64_t* capacity) {
+    if (!pt || !dev_ptr) return fail(TTVB_E_INVALID, "null argument");
+    const ttvb::PTState& S = pt->S;
+    const int64_t B = (int64_t)S.ntemps * (S.nwalkers / 2);
+    *dev_ptr = S.qlogl;
+    if (n) *n = B;
+    if (capacity) *capacity = B + 64;
     return TTVB_OK;
 }
 

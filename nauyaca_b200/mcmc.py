@@ -49,10 +49,12 @@ def make_sampler(PSystem, p0, betas=None, tmax=None, logprior=None, evaluate=Non
     return Sampler(batch_logl=evaluate, batch_logp=blp, **kw)
 
 
-def make_device_sampler(PSystem, p0, betas=None, tmax=None, seed=None, device=None):
+def make_device_sampler(PSystem, p0, betas=None, tmax=None, seed=None, device=None, shard=False, group=None):
     """The same set-up with every sampler move on the GPU (flat prior only): see
     ptsampler.DeviceSampler. The per-iteration host work disappears; use ``advance(n)`` to run
-    n iterations between two looks at the state."""
+    n iterations between two looks at the state. shard=True (one process per GPU, torch.distributed
+    initialised, same seed and p0 on every rank): the proposals of every half-step are split over
+    the ranks and their log-likelihoods all-gathered."""
     from .ptsampler import DeviceSampler
     p0 = np.asarray(p0, dtype=float)
     ntemps, nwalkers, ndim = p0.shape
@@ -61,7 +63,7 @@ def make_device_sampler(PSystem, p0, betas=None, tmax=None, seed=None, device=No
     p0_norm = bool(((p0 >= 0.0) & (p0 <= 1.0)).all())
     eng = _u.engine_for(PSystem, device=device)
     return DeviceSampler(eng, nwalkers, ntemps=ntemps, Tmax=tmax, betas=betas, a=10, adaptation_lag=1000.0,
-                         adaptation_time=100.0, seed=seed, cube=p0_norm)
+                         adaptation_time=100.0, seed=seed, cube=p0_norm, shard=shard, group=group)
 
 
 def pt_sample(PSystem, p0, iterations, thin=1, **kw):

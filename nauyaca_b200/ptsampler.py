@@ -381,7 +381,11 @@ class DeviceSampler:
     acceptance_fraction, tswap_acceptance_fraction, get_autocorr_time())."""
 
     def __init__(self, engine, nwalkers, ntemps=None, Tmax=None, betas=None, a=2.0, adaptation_lag=10000,
-                 adaptation_time=100, seed=None, cube=True):
+                 adaptation_time=100, seed=None, cube=True, group=None, shard=False):
+        """shard=True (with torch.distributed initialised, one process per GPU): the proposals of
+        every half-step are split over the ranks of `group` and their log-likelihoods
+        all-gathered (NCCL; host staging under gloo). Every rank must be given the same seed and
+        the same p0, and then holds the same ensemble at every iteration."""
         import ctypes as C
         from . import _lib
         self._C, self._lib = C, _lib
@@ -404,6 +408,13 @@ class DeviceSampler:
         self._time = 0
         self._started = False
         self._chain = self._logposterior = self._loglikelihood = self._beta_history = None
+        self._world, self._rank, self._group = 1, 0, group
+        if shard:
+            import torch.distributed as dist
+            if dist.is_initialized():
+                self._world, self._rank = dist.get_world_size(group), dist.get_rank(group)
+            if self._world > 1 and seed is None:
+                raise ValueError('a sharded DeviceSampler needs the same explicit seed on every rank')
         shape = (self.ntemps, self.nwalkers)
         self._p = np.empty(shape + (self.dim,)); self._logl = np.empty(shape)
         self.nprop = np.zeros(shape); self.nprop_accepted = np.zeros(shape)
@@ -457,7 +468,7 @@ class DeviceSampler:
                 self._loglikelihood = np.concatenate((self._loglikelihood, z(self.ntemps, self.nwalkers, nsave)), axis=2)
                 self._beta_history = np.concatenate((self._beta_history, z(self.ntemps, nsave)), axis=1)
         for _ in range(iterations):
-            self._lib.check(L.ttvb_pt_run(self._pt, 1, 1 if adapt else 0, None))
+            self._run(1, adapt)
             p, logpost, logl = self._fetch()
             if (self._time + 1) % thin == 0 and storechain:
                 self._chain[:, :, isave, :] = p
@@ -473,9 +484,53 @@ class DeviceSampler:
         nauyaca only looks at the state every `intra_steps` iterations, mcmc.py:227-229)."""
         if not self._started:
             raise ValueError('Initial walker positions not specified.')
-        self._lib.check(self._lib.lib().ttvb_pt_run(self._pt, int(iterations), 1 if adapt else 0, None))
+        self._run(int(iterations), adapt)
         self._time += int(iterations)
         return self._fetch()
+
+    # ---- iteration drivers
+    def _run(self, iterations, adapt):
+        L, chk = self._lib.lib(), self._lib.check
+        if self._world == 1:
+            chk(L.ttvb_pt_run(self._pt, int(iterations), 1 if adapt else 0, None))
+            return
+        lo, hi = self._shard_range()
+        for _ in range(int(iterations)):
+            for half in (0, 1):
+                chk(L.ttvb_pt_half_begin(self._pt, half, lo, hi, None))
+                self._gather_proposal_logl()
+                chk(L.ttvb_pt_half_end(self._pt, half, 1 if adapt else 0, None))
+
+    def _shard_range(self):
+        """Equal chunks of ceil(B / world) proposals (the last ones may be short or empty), so
+        that the all-gather can run in place on the padded device buffer."""
+        B = self.ntemps * (self.nwalkers // 2)
+        self._chunk = -(-B // self._world)
+        lo = min(B, self._rank * self._chunk)
+        return lo, min(B, lo + self._chunk)
+
+    def _gather_proposal_logl(self):
+        import torch
+        import torch.distributed as dist
+        C = self._C
+        if getattr(self, "_qbuf", None) is None:
+            ptr, n, cap = C.c_void_p(), C.c_int64(), C.c_int64()
+            self._lib.check(self._lib.lib().ttvb_pt_proposal_logl(self._pt, C.byref(ptr), C.byref(n), C.byref(cap)))
+            need = self._chunk * self._world
+            if need > cap.value:
+                raise ValueError(f'world size {self._world} too large for the proposal buffer')
+
+            class _Dev:
+                __cuda_array_interface__ = {"shape": (need,), "typestr": "<f8", "data": (ptr.value, False), "version": 2}
+            self._qbuf = torch.as_tensor(_Dev(), device=f"cuda:{self.engine.device}")
+        q, c, r = self._qbuf, self._chunk, self._rank
+        mine = q.narrow(0, r * c, c)
+        if dist.get_backend(self._group) == "nccl":
+            dist.all_gather_into_tensor(q, mine, group=self._group)          # in place, over NVLink
+        else:                                                                # gloo (CPU-side tests): host staging
+            out = torch.empty(c * self._world, dtype=torch.float64)
+            dist.all_gather_into_tensor(out, mine.cpu(), group=self._group)
+            q.copy_(out)
 
     run_mcmc = Sampler.run_mcmc
     betas = property(lambda self: self._betas)

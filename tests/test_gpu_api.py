@@ -1,5 +1,7 @@
 """GPU: the host-side mirror of the reference interface (nauyaca_b200.utils, GpuPool, DE seam)
 through the C ABI, against the goldens and the oracle."""
+import os
+
 import numpy as np
 import pytest
 
@@ -166,3 +168,33 @@ def test_device_sampler(systems, known, spec_ps, oracle):
     assert abs(rd.acceptance_fraction[0].mean() - host.acceptance_fraction[0].mean()) < 0.12
     for s in (dev, dev2, dev3, rd):
         s.close()
+
+
+def test_device_sampler_sharded(systems, known, spec_ps, tmp_path):
+    """The device sampler with the proposals of every half-step sharded over two ranks and the
+    proposal log-likelihoods all-gathered (ttvb_pt_half_begin / _end): both ranks end with the
+    ensemble of the unsharded sampler, bit for bit."""
+    import subprocess
+    import sys
+    import nauyaca_b200 as nb
+    import bench
+    spec = systems["doc2"]; PS = spec_ps(spec)
+    c = bench.cube_of(spec, known["G4"]["flat_params"])
+    rng = np.random.mtrand.RandomState(11)
+    nt, nw, dim = 5, 46, spec["ndim"]              # 115 proposals per half-step: uneven shards (58 + 57)
+    p0 = np.clip(c[None, None, :] + 0.01 * rng.normal(size=(nt, nw, dim)), 0, 1)
+    one = nb.mcmc.make_device_sampler(PS, p0, tmax=50.0, seed=1234)
+    next(one.sample(p0, iterations=1, adapt=True, storechain=False))
+    p, logpost, logl = one.advance(24, adapt=True)
+    np.save(tmp_path / "p0.npy", p0)
+    port = str(29600 + os.getpid() % 300)
+    worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_shard_sampler_worker.py")
+    procs = [subprocess.Popen([sys.executable, worker, str(r), "2", port, str(tmp_path / f"r{r}.npz"),
+                               str(tmp_path / "p0.npy")]) for r in range(2)]
+    for pr in procs:
+        assert pr.wait(timeout=300) == 0
+    for r in range(2):
+        z = np.load(tmp_path / f"r{r}.npz")
+        assert np.array_equal(z["p"], p) and np.array_equal(z["logl"], logl)
+        assert np.array_equal(z["betas"], one.betas) and np.array_equal(z["nacc"], one.nprop_accepted)
+    one.close()
