@@ -1,44 +1,48 @@
 #!/usr/bin/env python
 """Development tool: where the warp-stall samples of ttvb_main_kernel go.
 
-    ncu -i rep.ncu-rep --page source --csv --print-source cuda,sass > src.csv
-    python scripts/profile_regions.py src.csv <warp-steps per launch> [top]
+    ncu -i rep.ncu-rep --page source --csv --print-source sass > sass.csv
+    python scripts/profile_regions.py sass.csv <warp-steps per launch>
 
-Splits the SASS instructions into those executed about once per warp-step (the step loop) and
-the rest (event push, refinement, fold), and lists the rest by source line."""
+Every SASS instruction appears once in this view (the cuda,sass view repeats an instruction
+under every line of its inline stack). Instructions are bucketed by how often they execute per
+warp-step: ~1 = the step loop; the rest is the event path (push, refinement, fold), the rare
+Kepler iterations and prologue/epilogue. Within the step loop the samples are split by pipe."""
 import collections
 import csv
+import re
 import sys
 
-path, warpsteps = sys.argv[1], float(sys.argv[2])
-top = int(sys.argv[3]) if len(sys.argv) > 3 else 30
+path, W = sys.argv[1], float(sys.argv[2])
 rows = list(csv.reader(open(path)))
-cur = hdr = line = None
-agg = {}
-for r in rows:
-    if r and r[0] == 'File Path':
-        cur = r[1].split('/')[-1]; continue
-    if r and r[0] == 'Line No':
-        hdr = r; iS = hdr.index('# Samples'); iE = hdr.index('Instructions Executed'); continue
-    if not hdr or not r or r[0] == 'Function Name':
-        continue
-    if r[0] != '':
-        line = (cur, int(r[0]), r[1].strip()[:90]); continue
-    try:
-        smp, exe = int(r[iS]), int(r[iE])
-    except ValueError:
-        continue
-    k = (line, exe > 0.85 * warpsteps)
-    agg[k] = agg.get(k, 0) + smp
-tot = sum(agg.values())
-main = sum(v for (l, m), v in agg.items() if m)
-print(f'samples {tot}; step-loop instructions {main / tot:.3f}; rest {1 - main / tot:.3f}')
-c = collections.Counter()
-for (l, m), v in agg.items():
-    if not m:
-        c[l[0]] += v
-print('rest by file:', {k: round(v / tot, 4) for k, v in c.items() if v / tot > 0.001})
-for m in (False, True):
-    print('--- top lines,', 'step loop' if m else 'rest')
-    for v, l in sorted([(v, l) for (l, mm), v in agg.items() if mm == m], reverse=True)[:top]:
-        print(f'{v / tot * 100:5.2f}% {l[0]}:{l[1]} {l[2]}')
+hdr, data = rows[1], rows[2:]
+iS, iE, iSrc = hdr.index('# Samples'), hdr.index('Instructions Executed'), hdr.index('Source')
+seq = [(r[iSrc].strip(), int(r[iS]), int(r[iE])) for r in data]
+tot = sum(s[1] for s in seq)
+print(f'kernel: {hdr and rows[0][1]}')
+print(f'samples {tot}, SASS instructions {len(seq)}, warp-steps {W:.0f}')
+
+
+def opcode(s):
+    return re.sub(r'^@!?U?P\d+\s+', '', s).split()[0].split('.')[0]
+
+
+print('-- by executions per warp-step')
+b, n = collections.Counter(), collections.Counter()
+for s, smp, exe in seq:
+    r = exe / W
+    key = '0.85-1.3 (step loop)' if 0.85 < r < 1.3 else ('<0.05' if r < 0.05 else ('0.05-0.85' if r < 0.85 else '>1.3'))
+    b[key] += smp; n[key] += 1
+for k in ('0.85-1.3 (step loop)', '>1.3', '0.05-0.85', '<0.05'):
+    print(f'  {k:22s} {n[k]:6d} instructions  {100 * b[k] / tot:5.1f} % of samples')
+main = [(s, smp) for s, smp, exe in seq if 0.85 < exe / W < 1.3]
+FP64 = ('DFMA', 'DMUL', 'DADD', 'DSETP', 'DMNMX')
+fp = [x for x in main if opcode(x[0]) in FP64]
+print(f'-- step loop: {len(main)} instructions per warp-step, {len(fp)} on the FP64 pipe '
+      f'({100 * sum(x[1] for x in fp) / tot:.1f} % of samples), {len(main) - len(fp)} others '
+      f'({100 * sum(x[1] for x in main if opcode(x[0]) not in FP64) / tot:.1f} %)')
+c, m = collections.Counter(), collections.Counter()
+for s, smp in main:
+    if opcode(s) not in FP64:
+        c[opcode(s)] += smp; m[opcode(s)] += 1
+print('   others by opcode: ' + ', '.join(f'{op} x{m[op]} {100 * v / tot:.2f}%' for op, v in c.most_common(10)))
