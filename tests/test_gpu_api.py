@@ -198,3 +198,17 @@ def test_device_sampler_sharded(systems, known, spec_ps, tmp_path):
         assert np.array_equal(z["p"], p) and np.array_equal(z["logl"], logl)
         assert np.array_equal(z["betas"], one.betas) and np.array_equal(z["nacc"], one.nprop_accepted)
     one.close()
+
+
+def test_notebook_flow_end_to_end(capsys):
+    """examples/fit_two_planets.py: optimizer chains -> init_walkers('Ladder') -> device PT MCMC on
+    the Documentation system; the chain must not lose the optimizers' best solution."""
+    import importlib.util
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "fit_two_planets.py")
+    spec = importlib.util.spec_from_file_location("fit_two_planets", path)
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    r = mod.fit(nsols=6, ntemps=4, nwalkers=40, iterations=40, seed=5, quiet=True)
+    capsys.readouterr()
+    assert r["p0"].shape == (4, 40, 11) and np.isfinite(r["logl"]).all()
+    assert np.isfinite(r["best_chi2"]) and r["best_chi2"] < 1e19            # every observed transit reproduced
+    assert r["best_chi2"] <= 1.5 * r["opt_chi2"][0] + 50.0
