@@ -229,6 +229,7 @@ int ttvb_create(const ttvb_system* sys, int device, ttvb_handle** out) {
     if (sys->nobs < 0) return fail(TTVB_E_INVALID, "nobs < 0");
     if (!(sys->dt > 0.0) || !std::isfinite(sys->t0) || !std::isfinite(sys->ftime))
         return fail(TTVB_E_INVALID, "need dt > 0 and finite t0, ftime");
+    if (!(sys->mstar > 0.0) || !std::isfinite(sys->mstar)) return fail(TTVB_E_INVALID, "need a finite mstar > 0");
     int ndev = ttvb_device_count();
     if (ndev <= 0) return fail(TTVB_E_NO_DEVICE, "no CUDA device available (libttvb has no CPU fallback)");
     if (device < 0 || device >= ndev) return fail(TTVB_E_NO_DEVICE, "device %d out of range (0..%d)", device, ndev - 1);

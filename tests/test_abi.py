@@ -43,6 +43,9 @@ def test_create_rejects_bad_arguments():
     s.npla, s.ndim, s.nconst = 2, 3, 3
     assert L.ttvb_create(C.byref(s), 0, C.byref(h)) == _lib.TTVB_E_INVALID
     assert b"7*npla" in L.ttvb_last_error()
+    s.ndim, s.nconst, s.dt, s.ftime = 11, 3, 0.1, 10.0
+    assert L.ttvb_create(C.byref(s), 0, C.byref(h)) == _lib.TTVB_E_INVALID      # mstar == 0
+    assert b"mstar" in L.ttvb_last_error()
 
 
 def test_sampler_rng_known_answers():
