@@ -379,7 +379,9 @@ __device__ __noinline__ bool run_steps(StepCtx<N>& cx, const double dt, const lo
         if (!pending) {
             if (k > k1) break;
             if (__ballot_sync(0xffffffffu, alive) == 0u) break;
-            if (alive) {
+            {
+                // every lane steps; one without a live system computes on whatever its registers
+                // hold, on the straight-line path (idle flag), and nothing of it is ever used
                 double* hs = hist + (size_t)((k - 1) & 1) * 6 * N * TTVB_RS + tid;
 #pragma unroll
                 for (int i = 0; i < N; i++)
@@ -390,7 +392,7 @@ __device__ __noinline__ bool run_steps(StepCtx<N>& cx, const double dt, const lo
                     }
                 double rj[N], irj[N];
                 map_B<N>(C, p, dt, rj, irj);
-                if (!map_A_after_B<N>(C, p, dt, rj, irj)) { status |= 2; alive = false; trigmask = 0; }
+                if (!map_A_after_B<N>(C, p, dt, rj, irj, !alive)) { status |= 2; alive = false; trigmask = 0; }
             }
             Tm2 = Tm1; Tm1 = Time; Time += dt;
         }
@@ -559,7 +561,7 @@ ttvb_main_kernel(const __grid_constant__ DevSys S) {
         bool alive = sys < S.B;
         int status = 0;
         SmemConsts<N> C{cst_s + tid};
-        State<N> p;
+        State<N> p = {};
         double prev_dot[N];
         int count[N];
         int trigmask = 0, nev = 0;
