@@ -3,7 +3,7 @@
 // per planet (ttvb_lane.cuh). Checks that both end in the same bits and times them at full
 // occupancy and for a lone warp.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -fmad=false -std=c++17 -lineinfo \
-//        -I nauyaca_b200/csrc -o scripts/microbench/lane_step scripts/microbench/lane_step.cu
+//        -o scripts/microbench/lane_step scripts/microbench/lane_step.cu
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>

@@ -12,7 +12,7 @@
 // dependent-issue latency). One planet per lane needs about 100 registers, so 16-20 warps are
 // resident and the scheduler always finds an independent FP64 instruction.
 #pragma once
-#include "ttvb_math.cuh"
+#include "../../nauyaca_b200/csrc/ttvb_math.cuh"
 
 namespace ttvb {
 
