@@ -81,15 +81,16 @@ struct DevSys {
     long long ctx_stride;
 };
 
-// ---- queue layout of one warp: 4 x QCAP ints, then (18N+3) x QCAP doubles (field-major, so that
-//      the refining lanes read coalesced). QCAP = 64: a batch is refined two events per lane in
-//      lockstep (two independent dependency chains per lane).
+// ---- queue layout of one warp: QCAP slots, slot-major. Header int4 (owner, planet, epoch, seq) per
+//      slot, then SD doubles per slot: 3 states x N planets x 6 (x, v), T3, one pad (every pair
+//      of doubles is 16-byte aligned: the pusher writes and the refining lanes read 128 bits at a
+//      time, and the cooperative copy of the ring states is one coalesced store).
+//      QCAP = 64: a batch is refined two events per lane in lockstep.
 #define TTVB_QCAP 64
 template <int N>
 struct QLayout {
-    static constexpr int NI = 4;                    // owner, planet, epoch, seq
-    static constexpr int ND = 18 * N + 3;           // 3 states x N planets x 6, then T3
-    static constexpr long long BYTES = (long long)TTVB_QCAP * (NI * 4 + ND * 8);
+    static constexpr int SD = 18 * N + 4;
+    static constexpr long long BYTES = (long long)TTVB_QCAP * (16 + SD * 8);
 };
 
 // per-thread Kepler constants in shared memory: field f of planet i at [(f*N+i)*TPB + tid]
@@ -117,8 +118,12 @@ __device__ __forceinline__ unsigned long long q_policy() {
 __device__ __forceinline__ void q_st(double* p, double v, unsigned long long pol) {
     asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
 }
-__device__ __forceinline__ void q_st(int* p, int v, unsigned long long pol) {
-    asm volatile("st.global.L2::cache_hint.s32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
+__device__ __forceinline__ void q_st2(double* p, double a, double b, unsigned long long pol) {
+    asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(a), "d"(b), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void q_st4(int* p, int a, int b, int c, int d, unsigned long long pol) {
+    asm volatile("st.global.L2::cache_hint.v4.s32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d),
+                 "l"(pol) : "memory");
 }
 
 struct WarpQ {
@@ -152,6 +157,7 @@ __device__ __noinline__ void process_batch(const DevSys& S, int count, WarpQ Q, 
                                            const int* obs_epoch_s, const double* obs_time_s,
                                            const double* obs_sigma_s) {
     constexpr int CAP = TTVB_QCAP;
+    constexpr int SD = QLayout<N>::SD;
     const int lane = threadIdx.x & 31;
     __syncwarp();
     bool act[2];
@@ -162,13 +168,12 @@ __device__ __noinline__ void process_batch(const DevSys& S, int count, WarpQ Q, 
         const int slot = lane + 32 * e;
         act[e] = slot < count;
         sl[e] = act[e] ? slot : (lane < count ? lane : 0);     // idle chains shadow a valid event
-        owner[e] = __ldcg(Q.qi + 0 * CAP + sl[e]);
-        planet[e] = __ldcg(Q.qi + 1 * CAP + sl[e]);
-        epoch[e] = __ldcg(Q.qi + 2 * CAP + sl[e]);
-        seq[e] = __ldcg(Q.qi + 3 * CAP + sl[e]);
+        const int4 hd = __ldcg(reinterpret_cast<const int4*>(Q.qi) + sl[e]);
+        owner[e] = hd.x; planet[e] = hd.y; epoch[e] = hd.z; seq[e] = hd.w;
         otid[e] = warp_base_tid + owner[e];
-#pragma unroll
-        for (int k = 0; k < 3; k++) T3[e][k] = __ldcg(Q.qd + (18 * N + k) * CAP + sl[e]);
+        const double* tq = Q.qd + (long long)sl[e] * SD + 18 * N;
+        const double2 t01 = __ldcg(reinterpret_cast<const double2*>(tq));
+        T3[e][0] = t01.x; T3[e][1] = t01.y; T3[e][2] = __ldcg(tq + 2);
     }
     const double hdt = 0.5 * S.dt;
     // xs/vsn[e][0]: synchronised astrocentric state of the middle node k; [e][1]: of node k-1
@@ -191,12 +196,10 @@ __device__ __noinline__ void process_batch(const DevSys& S, int count, WarpQ Q, 
             MuArray<2> C;
 #pragma unroll
             for (int e = 0; e < 2; e++) {
-                const double* base = Q.qd + (long long)(which[e] * 6 * N + j * 6) * CAP + sl[e];
-#pragma unroll
-                for (int k = 0; k < 3; k++) {
-                    st.x[e][k] = __ldcg(base + k * CAP);
-                    st.v[e][k] = __ldcg(base + (3 + k) * CAP);
-                }
+                const double2* base = reinterpret_cast<const double2*>(Q.qd + (long long)sl[e] * SD + which[e] * 6 * N + j * 6);
+                const double2 a = __ldcg(base), b = __ldcg(base + 1), c = __ldcg(base + 2);
+                st.x[e][0] = a.x; st.x[e][1] = a.y; st.x[e][2] = b.x;
+                st.v[e][0] = b.y; st.v[e][1] = c.x; st.v[e][2] = c.y;
                 C.m[e] = kc_s[j * TTVB_TPB + otid[e]];
             }
             bool conv[2];
@@ -420,7 +423,7 @@ __device__ __noinline__ bool run_steps(StepCtx<N>& cx, const double dt, const lo
                     const bool nw = e >= 6 * N;
                     const int f = nw ? e - 6 * N : e;
                     cp_src[r] = f * TTVB_RS + (nw ? (6 * N * TTVB_RS - par_old) : par_old);
-                    cp_dst[r] = e * TTVB_QCAP;
+                    cp_dst[r] = e;
                 }
             }
 #pragma unroll 1
@@ -437,7 +440,7 @@ __device__ __noinline__ bool run_steps(StepCtx<N>& cx, const double dt, const lo
                             const int b = __ffs(mm) - 1;
                             mm &= mm - 1u;
                             const double* src = hist + (tid - lane + b);
-                            double* dst = qdq + (qcount + taken);
+                            double* dst = qdq + (qcount + taken) * QLayout<N>::SD;
                             taken++;
 #pragma unroll
                             for (int r = 0; r < CPR; r++)
@@ -449,22 +452,17 @@ __device__ __noinline__ bool run_steps(StepCtx<N>& cx, const double dt, const lo
                         int ci = 0;
 #pragma unroll
                         for (int j = 0; j < N; j++) if (j == i) { ci = count[j]; count[j] = ci + 1; }
-                        q_st(qi + 0 * TTVB_QCAP + slot, lane, pol);
-                        q_st(qi + 1 * TTVB_QCAP + slot, i, pol);
-                        q_st(qi + 2 * TTVB_QCAP + slot, ci, pol);
-                        q_st(qi + 3 * TTVB_QCAP + slot, nev, pol);
+                        q_st4(qi + 4 * slot, lane, i, ci, nev, pol);
                         nev++;
-                        double* qd = qdq + slot;
+                        double* qd = qdq + slot * QLayout<N>::SD + 2 * 6 * N;
 #pragma unroll
-                        for (int j = 0; j < N; j++)
-#pragma unroll
-                            for (int c = 0; c < 3; c++) {
-                                q_st(qd + (2 * 6 * N + j * 6 + c) * TTVB_QCAP, p.x[j][c], pol);
-                                q_st(qd + (2 * 6 * N + j * 6 + 3 + c) * TTVB_QCAP, p.v[j][c], pol);
-                            }
-                        q_st(qd + (18 * N + 0) * TTVB_QCAP, Tm2, pol);
-                        q_st(qd + (18 * N + 1) * TTVB_QCAP, Tm1, pol);
-                        q_st(qd + (18 * N + 2) * TTVB_QCAP, Time, pol);
+                        for (int j = 0; j < N; j++) {
+                            q_st2(qd + j * 6 + 0, p.x[j][0], p.x[j][1], pol);
+                            q_st2(qd + j * 6 + 2, p.x[j][2], p.v[j][0], pol);
+                            q_st2(qd + j * 6 + 4, p.v[j][1], p.v[j][2], pol);
+                        }
+                        q_st2(qd + 6 * N, Tm2, Tm1, pol);
+                        q_st(qd + 6 * N + 2, Time, pol);
                         t = false;
                         trigmask &= ~(1 << i);
                     }
@@ -541,7 +539,7 @@ ttvb_main_kernel(const __grid_constant__ DevSys S) {
         const long long gw = (long long)blockIdx.x * (TTVB_TPB / 32) + warp;
         unsigned char* qb = S.queue + gw * S.queue_stride;
         Q.qi = (int*)qb;
-        Q.qd = (double*)(qb + TTVB_QCAP * QLayout<N>::NI * 4);
+        Q.qd = (double*)(qb + TTVB_QCAP * 16);
     }
     const long long ntiles = (S.B + TTVB_TPB - 1) / TTVB_TPB;
     const int rowlen = S.rowlen;
