@@ -140,6 +140,41 @@ def test_queue_fills_in_the_middle_of_a_push(oracle):
     eng.close()
 
 
+def test_two_planets_trigger_in_the_same_step(oracle):
+    """Systems whose two inner planets transit in the same step (same period and phase, orbits
+    tilted apart), 31 copies per warp plus one unrelated system: a lane pushes two events at
+    once, and the queue runs out of room in front of such a pair (odd fill level). Bit for bit
+    against the oracle, chi2 and event table."""
+    import nauyaca_b200 as nb
+    spec = _spec(3, ftime=70.0)
+    eng = nb.BatchEngine(spec); osys = oracle.OracleSystem(spec)
+    twin = np.array([0.05, 5.0, 0.02, 88.0, 30.0, 100.0, 10.0,
+                     0.05, 5.0, 0.02, 92.0, 30.0, 100.0, 60.0,
+                     3.0, 11.3, 0.05, 89.5, 200.0, 40.0, 0.0])
+    rng = np.random.default_rng(3)
+    other = np.array([[2.0, 3.1 + 0.3 * k, 0.03, 89.8, 10.0 * k, 50.0 + 20 * k, 0.0,
+                       4.0, 6.9 + 0.2 * k, 0.04, 90.2, 80.0, 120.0 + 7 * k, 0.0,
+                       6.0, 13.0 + 0.5 * k, 0.01, 90.0, 150.0, 10.0 * k, 0.0] for k in range(4)])
+    rows = []
+    for w in range(4):
+        rows += [twin] * 31 + [other[w]]
+    X = np.array(rows)
+    chi2, logl, st = eng.loglike(X, mode=2)
+    o = osys.loglike(X, mode=2)
+    _same(chi2, o[0]); _same(logl, o[1]); _same(st, o[2])
+    n, pl, ep, tm, rs, vs, st2 = eng.ephemeris(X, mode=2, cap=128)
+    for b in (0, 30, 31, 32, 127):
+        ost, opl, oep, otm, ors, ovs = oracle.ephemeris(X[b], spec["mstar"], spec["t0"], spec["dt"], spec["ftime"], cap=128)
+        k = n[b]
+        assert st2[b] == ost and k == len(otm)
+        _same(pl[b, :k], opl); _same(ep[b, :k], oep); _same(tm[b, :k], otm); _same(rs[b, :k], ors)
+    # the twins really do transit in the same step: equal times for planets 0 and 1
+    k = n[0]
+    t0 = tm[0, :k][pl[0, :k] == 0]; t1 = tm[0, :k][pl[0, :k] == 1]
+    assert len(t0) > 5 and len(t0) == len(t1) and np.max(np.abs(t0 - t1)) < 0.02
+    eng.close()
+
+
 def test_chunked_host_batches(oracle):
     """More rows than the 2^20 staging chunk: host-pointer path loops over chunks."""
     import nauyaca_b200 as nb
