@@ -377,9 +377,11 @@ __device__ __noinline__ bool run_steps(StepCtx<N>& cx, const double dt, const lo
     long long k = cx.k;
     bool full = false;
     constexpr int CPR = (12 * N + 31) / 32;
+    // a call that comes back from a refinement in the middle of a push phase re-enters there
+    if (pending) { pending = false; goto push_phase; }
 #pragma unroll 1
     for (;;) {
-        if (!pending) {
+        {
             if (k > k1) break;
             if (__ballot_sync(0xffffffffu, alive) == 0u) break;
             {
@@ -399,7 +401,7 @@ __device__ __noinline__ bool run_steps(StepCtx<N>& cx, const double dt, const lo
             }
             Tm2 = Tm1; Tm1 = Time; Time += dt;
         }
-        pending = false;
+    push_phase:
         // ---- push the events triggered at step k-1 (they now have p_{k-2}, p_{k-1}, p_k). The two
         //      older states are in the ring: all 32 lanes copy them together, one field each; the
         //      owner adds p_k from its registers and the header.
