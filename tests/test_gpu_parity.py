@@ -200,3 +200,29 @@ def test_c4_full_size_properties(oracle):
     oc, ol, ost = osys.loglike(X[pick], mode=0)
     assert np.array_equal(oc, chi2[pick]) and np.array_equal(ol, logl[pick])
     eng.close()
+
+
+def test_c5_full_sweep_streams_in_chunks(oracle, systems):
+    """BASELINE config 5 at full size: the 10^7-point uniform sweep of the 3-planet system
+    (500 d, dt 0.34874) through the host-pointer path, which streams it in chunks of 2^20.
+    Size-independent properties (every chunk boundary included) and a sample against the
+    oracle, bit for bit."""
+    import nauyaca_b200 as nb
+    spec = systems["sys3"]
+    eng = nb.BatchEngine(spec); osys = oracle.OracleSystem(spec)
+    B = 10_000_000
+    rng = np.random.default_rng(20240607)
+    X = rng.random((B, spec["ndim"]))
+    chi2, logl, st = eng.loglike(X, mode=0)
+    assert chi2.shape == (B,) and np.all(chi2 > 0) and not np.isnan(chi2).any()
+    assert np.all((st & 1) == 0)                                        # U(0,1) walkers are inside the hypercube
+    assert np.array_equal(logl, -0.5 * chi2 - spec["second_term_sum"])
+    # every system is independent of its position in the batch, chunk boundaries included
+    edges = np.concatenate([np.arange(c - 40, c + 40) for c in range(1 << 20, B, 1 << 20)])
+    idx = np.concatenate([edges, rng.integers(0, B, 4000), [0, B - 1]])
+    chi2s, _, sts = eng.loglike(X[idx], mode=0)
+    assert np.array_equal(chi2s, chi2[idx]) and np.array_equal(sts, st[idx])
+    pick = idx[::200]
+    oc, ol, ost = osys.loglike(X[pick], mode=0)
+    assert np.array_equal(oc, chi2[pick]) and np.array_equal(ost, st[pick])
+    eng.close()
