@@ -261,6 +261,8 @@ class ClockSampler:
 
 # ----------------------------------------------------------------------------- GPU side
 def run_gpu(args):
+    from nauyaca_b200 import _lib as _ttvb_lib
+    _ttvb_lib.ensure_built(builder=int(os.environ.get("LOCAL_RANK", "0")) == 0)
     import torch
     import nauyaca_b200 as nb
 
@@ -417,6 +419,8 @@ def run_gpu(args):
 
 
 def run_c3(args):
+    from nauyaca_b200 import _lib as _ttvb_lib
+    _ttvb_lib.ensure_built(builder=int(os.environ.get("LOCAL_RANK", "0")) == 0)
     """BASELINE configs[2]: the ptemcee-style MCMC itself. A step = one full PT iteration of
     10 temperatures x 1000 walkers (two half-ensemble stretch moves of 5000 proposals each,
     temperature swaps, ladder adaptation) through nauyaca_b200.mcmc.make_sampler; host sampler

@@ -62,8 +62,29 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, SRC]
+    tmp = LIB_PATH + f".tmp{os.getpid()}"
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp, SRC]
     subprocess.check_call(cmd)
+    os.replace(tmp, LIB_PATH)          # readers never see a half-written library
+    return LIB_PATH
+
+
+def ensure_built(builder=True, timeout_s=600.0):
+    """Build libttvb.so if it is missing or older than its sources (entry points that may run on a
+    fresh checkout call this: the test session, bench.py, smoke()). Not a fallback: what gets
+    built is the CUDA library, and without nvcc this raises. builder=False (ranks other than the
+    first of a multi-process launch): wait for the builder instead of building."""
+    if "TTVB_LIB" in os.environ or not needs_build():
+        return LIB_PATH
+    if builder:
+        build(force=True)
+        return LIB_PATH
+    import time
+    t0 = time.time()
+    while needs_build():
+        if time.time() - t0 > timeout_s:
+            raise TTVBError(f"{LIB_PATH} was not built within {timeout_s:.0f} s")
+        time.sleep(0.5)
     return LIB_PATH
 
 

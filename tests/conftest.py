@@ -14,6 +14,8 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    from nauyaca_b200 import _lib
+    _lib.ensure_built()          # nvcc cross-compiles without a GPU; a fresh checkout has no libttvb.so
 
 
 def has_gpu():
