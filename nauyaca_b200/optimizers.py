@@ -4,8 +4,9 @@
 process each (optimizers.py:185-189); every chain calls ``calculate_chi2`` one vector at a
 time, so the reference evaluates at most ``cores`` vectors concurrently. Here the SAME scipy
 calls (same algorithms, same options as optimizers.py:78-113) run one per Python thread, and
-their objective calls meet in a *rendezvous*: whenever every live chain is waiting for a
-value, all pending vectors are evaluated in ONE ``ttvb_loglike`` batch. A DE generation
+their objective calls meet in a *rendezvous*: all pending vectors are evaluated in ONE
+``ttvb_loglike`` batch, as soon as the coordinator is free (default) or whenever every live chain
+is waiting for a value (``greedy=False``). A DE generation
 (vectorised scipy objective) contributes 30*ndim vectors per chain, Powell and Nelder-Mead
 one vector per chain and round.
 
@@ -30,8 +31,12 @@ class RendezvousBatcher:
     ``batch_fn(X[M, ndim]) -> f[M]`` call and hands the slices back. Every worker sleeps on its
     own Event (no thundering herd on a shared condition variable)."""
 
-    def __init__(self, batch_fn, nworkers):
+    def __init__(self, batch_fn, nworkers, greedy=True):
+        """greedy: a batch goes out as soon as the coordinator is free and anything is pending
+        (the launch in flight hides the host work of the other chains; launches are latency-bound,
+        so their size does not matter), instead of waiting until every live chain has asked."""
         self.batch_fn = batch_fn
+        self.greedy = bool(greedy)
         self.live = int(nworkers)
         self.lock = threading.Lock()
         self.ready = threading.Event()     # "every live worker is waiting" or "a worker left"
@@ -51,7 +56,7 @@ class RendezvousBatcher:
             if self.error is not None:
                 raise RuntimeError("batch evaluation failed") from self.error
             self.pending.append((X, holder))
-            if len(self.pending) >= self.live:
+            if self.greedy or len(self.pending) >= self.live:
                 self.ready.set()
         ev.wait()
         if holder["f"] is None:
@@ -70,7 +75,7 @@ class RendezvousBatcher:
                 self.ready.clear()
                 if self.live <= 0 and not self.pending:
                     return
-                if len(self.pending) < self.live or not self.pending:
+                if not self.pending or (not self.greedy and len(self.pending) < self.live):
                     continue
                 todo, self.pending = self.pending, []
             try:
@@ -133,7 +138,8 @@ def _chain(PSystem_bounds, ndim, evaluate, seed, de_opts, powell_opts, nm_opts, 
         batcher.worker_done()
 
 
-def de_pw_nm(PSystem, nsols, seed=None, evaluate=None, powell=True, de_opts=None, powell_opts=None, nm_opts=None):
+def de_pw_nm(PSystem, nsols, seed=None, evaluate=None, powell=True, de_opts=None, powell_opts=None, nm_opts=None,
+             greedy=True):
     """``nsols`` DE -> Powell -> Nelder-Mead chains in lock-step batches.
 
     Returns a list of ``[f, x_cube(list), x_phys(list)]`` like ``Optimizers.DE_PW_NM``
@@ -153,7 +159,7 @@ def de_pw_nm(PSystem, nsols, seed=None, evaluate=None, powell=True, de_opts=None
     pw_o.update(powell_opts or {})
     nm_o = dict(maxiter=15000, maxfev=15000, xatol=0.0001, fatol=1, disp=False, adaptive=True)
     nm_o.update(nm_opts or {})
-    batcher = RendezvousBatcher(evaluate, nsols)
+    batcher = RendezvousBatcher(evaluate, nsols, greedy=greedy)
     out = [None] * nsols
     ss = np.random.SeedSequence(seed)
     seeds = [int(s.generate_state(1)[0]) for s in ss.spawn(nsols)]

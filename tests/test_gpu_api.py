@@ -113,7 +113,8 @@ def test_batched_optimizer_chains_on_gpu(systems, spec_ps, oracle):
     """optimizers.py:46-139 seam: DE -> Powell -> Nelder-Mead chains in rendezvous batches."""
     import nauyaca_b200 as nb
     spec = systems["doc2"]; PS = spec_ps(spec); osys = oracle.OracleSystem(spec)
-    out = nb.optimizers.run_optimizers(PS, nsols=8, seed=7, powell_opts={"maxfev": 300}, nm_opts={"maxfev": 500})
+    out = nb.optimizers.run_optimizers(PS, nsols=8, seed=7, powell_opts={"maxfev": 300}, nm_opts={"maxfev": 500},
+                                       greedy=False)
     assert out["chi2"].shape == (8,) and np.all(np.diff(out["chi2"]) >= 0)
     # every reported chi2 is the oracle's chi2 of the reported cube vector, bit for bit
     ref = osys.loglike(out["cube"], mode=0)[0]
@@ -122,6 +123,10 @@ def test_batched_optimizer_chains_on_gpu(systems, spec_ps, oracle):
     assert all(s[2] <= s[1] <= s[0] for s in st)                        # each stage improves
     assert max(out["info"]["batches"]) == 8 * 30 * spec["ndim"]         # a DE generation of all chains in one launch
     assert out["physical"].shape == (8, spec["ndim"])
+    # the default (greedy) batching policy changes how the evaluations are grouped, not what they return
+    g = nb.optimizers.run_optimizers(PS, nsols=8, seed=7, powell_opts={"maxfev": 300}, nm_opts={"maxfev": 500})
+    assert np.array_equal(g["chi2"], out["chi2"]) and np.array_equal(g["cube"], out["cube"])
+    assert sum(g["info"]["batches"]) == sum(out["info"]["batches"])
 
 
 def test_device_sampler(systems, known, spec_ps, oracle):

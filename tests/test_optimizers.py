@@ -26,7 +26,7 @@ def test_rendezvous_batches_all_waiting_workers():
     def batch(X):
         calls.append(X.shape[0])
         return X.sum(axis=1)
-    b = RendezvousBatcher(batch, 5)
+    b = RendezvousBatcher(batch, 5, greedy=False)
     res = {}
 
     def work(i):
@@ -71,9 +71,15 @@ def test_chains_equal_serial_scipy_and_are_batched():
     PS = _PS(4)
     nsols = 6
     res, info = de_pw_nm(PS, nsols, seed=123, evaluate=_rosen_like,
-                         powell_opts={"maxfev": 400}, nm_opts={"maxfev": 600})
+                         powell_opts={"maxfev": 400}, nm_opts={"maxfev": 600}, greedy=False)
     assert max(info["batches"]) == nsols * 30 * 4                     # a DE generation of every chain at once
     assert np.median(info["batches"]) >= 2
+    # the greedy policy (default: a batch leaves as soon as the coordinator is free) groups the same
+    # evaluations differently and returns the same chains
+    res_g, info_g = de_pw_nm(PS, nsols, seed=123, evaluate=_rosen_like,
+                             powell_opts={"maxfev": 400}, nm_opts={"maxfev": 600})
+    assert sum(info_g["batches"]) == sum(info["batches"])
+    assert all(a[0] == b[0] and a[1] == b[1] for a, b in zip(res, res_g))
     ss = np.random.SeedSequence(123)
     seeds = [int(s.generate_state(1)[0]) for s in ss.spawn(nsols)]
     for i in range(nsols):
