@@ -405,7 +405,8 @@ __device__ __noinline__ bool run_steps(StepCtx<N>& cx, const double dt, const lo
         // ---- push the events triggered at step k-1 (they now have p_{k-2}, p_{k-1}, p_k). The two
         //      older states are in the ring: all 32 lanes copy them together, one field each; the
         //      owner adds p_k from its registers and the header.
-        if (__ballot_sync(0xffffffffu, trigmask != 0) != 0u) {
+        unsigned pm = __reduce_or_sync(0xffffffffu, (unsigned)trigmask);     // planets that triggered somewhere in the warp
+        if (pm != 0u) {
             __syncwarp();
             const unsigned long long pol = q_policy();
             const int par_old = (int)(k & 1) * 6 * N * TTVB_RS;     // ring slot of p_{k-2}; the other holds p_{k-1}
@@ -428,8 +429,9 @@ __device__ __noinline__ bool run_steps(StepCtx<N>& cx, const double dt, const lo
                     cp_dst[r] = e;
                 }
             }
-#pragma unroll 1
-            for (int i = 0; i < N && !full; i++) {
+            while (pm != 0u && !full) {
+                const int i = __ffs(pm) - 1;
+                pm &= pm - 1u;
                 bool t = (trigmask >> i) & 1;
                 unsigned m = __ballot_sync(0xffffffffu, t);
                 while (m) {
