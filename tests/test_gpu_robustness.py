@@ -36,7 +36,7 @@ def _same(a, b):
     assert ok.all(), f"{(~ok).sum()} of {a.size} differ: {a[~ok][:3]} vs {b[~ok][:3]}"
 
 
-@pytest.mark.parametrize("npla", [1, 2, 4, 5])
+@pytest.mark.parametrize("npla", [1, 2, 4, 5, 7, 9])
 def test_other_planet_counts(oracle, npla):
     import nauyaca_b200 as nb
     spec = _spec(npla)
