@@ -48,6 +48,7 @@ class SpecSystem:
         from collections import OrderedDict
         self.system_name = spec.get("system_name", "")
         self.mstar, self.rstarAU = spec["mstar"], spec["rstarAU"]
+        self.rstar = spec.get("rstar")
         self.t0, self.ftime, self.dt = spec["t0"], spec["ftime"], spec["dt"]
         self.npla, self.ndim = spec["npla"], spec["ndim"]
         self.planets_IDs = dict(spec.get("planets_IDs", {p: o["planet_index"] for p, o in spec["observed"].items()}))

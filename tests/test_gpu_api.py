@@ -217,3 +217,33 @@ def test_notebook_flow_end_to_end(capsys):
     assert r["p0"].shape == (4, 40, 11) and np.isfinite(r["logl"]).all()
     assert np.isfinite(r["best_chi2"]) and r["best_chi2"] < 1e19            # every observed transit reproduced
     assert r["best_chi2"] <= 1.5 * r["opt_chi2"][0] + 50.0
+
+
+def test_run_mcmc_device_sampler(systems, known, spec_ps, oracle, tmp_path):
+    """mcmc.run_mcmc (the reference's MCMC.run bookkeeping) over the device-resident sampler: the
+    record holds the ensemble at every intra_steps-th iteration of the same-seed sampler."""
+    import nauyaca_b200 as nb
+    import bench
+    spec = systems["doc2"]; PS = spec_ps(spec); osys = oracle.OracleSystem(spec)
+    c = bench.cube_of(spec, known["G4"]["flat_params"])
+    rng = np.random.mtrand.RandomState(2)
+    nt, nw, dim = 4, 30, spec["ndim"]
+    p0 = np.clip(c[None, None, :] + 0.01 * rng.normal(size=(nt, nw, dim)), 0, 1)
+    s, rec = nb.mcmc.run_mcmc(PS, p0, itmax=14, intra_steps=4, tmax=30.0, seed=99, path=str(tmp_path) + "/",
+                              file_name="dev")
+    assert rec["CHAINS"].shape == (nt, nw, 4, dim) and rec["INDEX"][0] == 2 and rec["ITER_LAST"][0] == 12
+    ref = nb.mcmc.make_device_sampler(PS, p0, tmax=30.0, seed=99)
+    next(ref.sample(p0, iterations=1, adapt=True, storechain=False))
+    state = ref.advance(3, adapt=True)
+    for k in range(3):
+        p, lp, ll = state
+        assert np.array_equal(rec["CHAINS"][:, :, k, :], p)
+        assert rec["MAP"][k] == lp.max() and rec["MEANLOGPOST"][k] == np.mean(lp[0])
+        i, j = np.unravel_index(np.flatnonzero(lp.ravel() == lp.max())[-1], lp.shape)
+        assert np.array_equal(rec["BESTSOLS"][k], p[i][j])
+        assert np.array_equal(rec["BETAS"][k], ref.betas)
+        assert osys.loglike(rec["BESTSOLS"][k][None, :], mode=0)[1][0] * ref.betas[i] == rec["MAP"][k]
+        state = ref.advance(4, adapt=True)
+    assert np.all(rec["CHAINS"][:, :, 3, :] == 0)                      # the slot the reference leaves empty
+    assert os.path.exists(str(tmp_path) + "/dev.npz")
+    s.close(); ref.close()

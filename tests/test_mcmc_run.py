@@ -1,0 +1,75 @@
+"""The bookkeeping of the reference's MCMC.run loop (mcmc.py:218-312, 315-402) in
+nauyaca_b200.mcmc.run_mcmc: CPU test with the host sampler over the oracle; the device sampler
+is covered in tests/test_gpu_api.py."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import nauyaca_b200 as nb
+from conftest import GOLDEN
+
+
+def _setup(oracle):
+    with open(os.path.join(GOLDEN, "systems.json")) as fh:
+        spec = json.load(fh)["doc2"]
+    PS = nb.SpecSystem(spec)
+    osys = oracle.OracleSystem(spec)
+    rng = np.random.mtrand.RandomState(3)
+    p0 = np.clip(0.5 + 0.05 * rng.normal(size=(3, 24, spec["ndim"])), 0, 1)
+    mk = lambda: nb.mcmc.make_sampler(PS, p0, tmax=20.0, random=np.random.mtrand.RandomState(4),
+                                      evaluate=lambda X: osys.loglike(X, mode=0)[1])
+    return spec, PS, osys, p0, mk
+
+
+def test_record_follows_the_reference_loop(oracle, tmp_path):
+    spec, PS, osys, p0, mk = _setup(oracle)
+    itmax, intra = 13, 3
+    s, rec = nb.mcmc.run_mcmc(PS, p0, itmax=itmax, intra_steps=intra, tmax=20.0, sampler=mk(),
+                              path=str(tmp_path) + "/", file_name="run", suffix="_a")
+    nsteps = -(-itmax // intra)
+    nlooks = itmax // intra
+    assert rec["CHAINS"].shape == (3, 24, nsteps, spec["ndim"]) and rec["BETAS"].shape == (nsteps, 3)
+    assert rec["INDEX"][0] == nlooks - 1 and rec["ITER_LAST"][0] == nlooks * intra
+    # the same loop by hand: sampler.sample(thin=intra_steps), a look every intra_steps iterations
+    ref = mk()
+    k = 0
+    for it, (p, lp, ll) in enumerate(ref.sample(p0=p0, iterations=itmax, thin=intra, storechain=True, adapt=True)):
+        if (it + 1) % intra:
+            continue
+        assert np.array_equal(rec["CHAINS"][:, :, k, :], p) and np.array_equal(rec["CHAINS"][:, :, k, :], ref.chain[:, :, k, :])
+        mx, (i, j) = max((x, (i, j)) for i, row in enumerate(lp) for j, x in enumerate(row))     # mcmc.py:235-237
+        assert rec["MAP"][k] == mx and np.array_equal(rec["BESTSOLS"][k], p[i][j])
+        assert rec["MEANLOGPOST"][k] == np.mean(lp[0])
+        assert np.array_equal(rec["BETAS"][k], ref.betas)
+        assert np.array_equal(rec["ACC_FRAC0"][k], ref.tswap_acceptance_fraction)
+        assert rec["AUTOCORR"][k] == np.mean(ref.get_autocorr_time()[0])
+        k += 1
+    assert k == nlooks
+    assert np.all(rec["CHAINS"][:, :, nlooks:, :] == 0)                  # the slot the reference leaves empty
+    # every stored walker with its stored MAP: logpost = beta * logl (flat prior)
+    ll = osys.loglike(rec["BESTSOLS"][:nlooks], mode=0)[1]
+    assert np.all(np.isfinite(ll))
+    # constants and names
+    assert rec["NDIM"][0] == spec["ndim"] and rec["NTEMPS"][0] == 3 and rec["NWALKERS"][0] == 24
+    assert rec["ITMAX"][0] == itmax and rec["INTRA_STEPS"][0] == intra and rec["NPLA"][0] == 2
+    assert np.array_equal(rec["p0"], p0) and np.array_equal(rec["BOUNDS"], np.array(spec["bounds"]))
+    # the file
+    z = np.load(str(tmp_path) + "/run_a.npz")
+    for key in ("CHAINS", "AUTOCORR", "BETAS", "ACC_FRAC0", "INDEX", "ITER_LAST", "BESTSOLS", "MAP", "MEANLOGPOST",
+                "p0", "BOUNDS", "NDIM", "NTEMPS", "NWALKERS", "ITMAX", "INTRA_STEPS", "REF_EPOCH", "NPLA", "MSTAR", "RSTAR"):
+        assert np.array_equal(z[key], rec[key], equal_nan=True), key
+    assert str(z["NAME"]) == rec["NAME"]
+
+
+def test_argument_checks(oracle, tmp_path):
+    spec, PS, osys, p0, mk = _setup(oracle)
+    with pytest.raises(RuntimeError, match="nwalkers have to be >= 22"):
+        nb.mcmc.run_mcmc(PS, p0[:, :20], sampler=mk(), save=False)
+    with pytest.raises(RuntimeError, match="differs from that in 'p0'"):
+        nb.mcmc.run_mcmc(PS, p0[:, :, :10], sampler=mk(), save=False)
+    with pytest.raises(RuntimeError, match="differs from number of temperatures"):
+        nb.mcmc.run_mcmc(PS, p0, betas=[1.0, 0.5], sampler=mk(), save=False)
+    with pytest.raises(RuntimeError, match="does not exist"):
+        nb.mcmc.run_mcmc(PS, p0, sampler=mk(), path=str(tmp_path) + "/nowhere/")
