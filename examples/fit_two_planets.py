@@ -36,25 +36,28 @@ def fit(nsols=16, ntemps=10, nwalkers=200, iterations=300, seed=3, quiet=False):
     np.random.seed(seed)
     p0 = nb.utils.init_walkers(PS, distribution="Ladder", opt_data={"chi2": opt["chi2"], "cube": opt["cube"]},
                                ntemps=ntemps, nwalkers=nwalkers, fbest=0.5)
-    # ---- MCMC(PS, p0=p0, tmax=..., itmax=...).run()  (mcmc.py:141-312), sampler moves on the device
-    sampler = nb.mcmc.make_device_sampler(PS, p0, tmax=100.0, seed=seed)
+    # ---- MCMC(PS, p0=p0, tmax=..., itmax=..., intra_steps=...).run()  (mcmc.py:141-312), sampler moves
+    #      on the device; rec is the record the reference keeps in its HDF5 file (same names)
+    intra = max(1, iterations // 10)
     t0 = time.perf_counter()
-    next(sampler.sample(p0, iterations=1, adapt=True, storechain=False))
-    p, logpost, logl = sampler.advance(iterations - 1, adapt=True)
+    sampler, rec = nb.mcmc.run_mcmc(PS, p0, itmax=iterations, intra_steps=intra, tmax=100.0, seed=seed, save=False)
     dt = time.perf_counter() - t0
-    i = np.unravel_index(np.argmax(logl[0]), logl[0].shape)
-    best = p[0][i]
-    say(f"mcmc: {iterations} iterations of {ntemps} x {nwalkers} walkers in {dt:.2f} s "
-        f"({iterations * ntemps * nwalkers / dt:.0f} likelihood evaluations per second), "
-        f"cold-chain acceptance {sampler.acceptance_fraction[0].mean():.2f}, swaps {sampler.tswap_acceptance_fraction[0]:.2f}")
+    p, logpost, logl = sampler._fetch()
+    k = int(np.argmax(rec["MAP"][:rec["INDEX"][0] + 1]))
+    best = rec["BESTSOLS"][k]
+    say(f"mcmc: {int(rec['ITER_LAST'][0])} iterations of {ntemps} x {nwalkers} walkers in {dt:.2f} s "
+        f"({int(rec['ITER_LAST'][0]) * ntemps * nwalkers / dt:.0f} likelihood evaluations per second), "
+        f"cold-chain acceptance {sampler.acceptance_fraction[0].mean():.2f}, swaps {sampler.tswap_acceptance_fraction[0]:.2f}, "
+        f"mean log-posterior of the cold chain {rec['MEANLOGPOST'][0]:.1f} -> {rec['MEANLOGPOST'][rec['INDEX'][0]]:.1f}")
     chi2 = nb.utils.calculate_chi2(best, PS)
     phys = nb.utils.cube_to_physical(PS, best)
-    say(f"best walker: logL {logl[0][i]:.3f}, chi2 {chi2:.3f}")
+    say(f"maximum a posteriori over the run: log-posterior {rec['MAP'][k]:.3f}, chi2 {chi2:.3f}")
     say("physical parameters (mass[Mearth] period[d] ecc inc[deg] argument[deg] mean_anomaly[deg] ascending_node[deg]):")
-    for k in range(PS.npla):
-        say("   ", np.array2string(np.asarray(phys[7 * k:7 * k + 7]), precision=5))
+    for pl in range(PS.npla):
+        say("   ", np.array2string(np.asarray(phys[7 * pl:7 * pl + 7]), precision=5))
     sampler.close()
-    return {"opt_chi2": opt["chi2"], "best_chi2": float(chi2), "best_logl": float(logl[0][i]), "p0": p0, "logl": logl}
+    return {"opt_chi2": opt["chi2"], "best_chi2": float(chi2), "best_logl": float(rec["MAP"][k]), "p0": p0, "logl": logl,
+            "record": rec}
 
 
 if __name__ == "__main__":
