@@ -12,7 +12,7 @@ import numpy as np
 from . import utils as _u
 from .ptsampler import Sampler
 
-__all__ = ["make_sampler", "make_device_sampler", "pt_sample", "run_mcmc", "write_hdf5"]
+__all__ = ["make_sampler", "make_device_sampler", "pt_sample", "run_mcmc", "restart_mcmc", "write_hdf5"]
 
 
 def _logprior_zero(x, psystem=None):
@@ -213,3 +213,35 @@ def write_hdf5(rec, filename):
             else:
                 fh.create_dataset(key, val.shape, dtype=dt, compression="gzip", compression_opts=4)[...] = val
     return filename
+
+
+def restart_mcmc(PSystem, record_file, in_path="./", out_path="./", itmax=100, intra_steps=2, suffix="_2",
+                 restart_ladder=False):
+    """``MCMC.restart_mcmc`` (mcmc.py:404-500) for the records ``run_mcmc`` writes: the keyword
+    arguments that continue a run from its last saved ensemble -- ``run_mcmc(PSystem, **args)``.
+    The ladder is the last saved one, or the first (``restart_ladder=True``); the new file is the
+    old name plus ``suffix``. ``record_file``: the ``.npz`` (or, with h5py, ``.hdf5``) file name."""
+    import os
+    if not os.path.exists(out_path):
+        raise RuntimeError(f"directory {out_path} does not exists")
+    if not out_path.endswith("/"):
+        out_path += "/"
+    if record_file == "":
+        raise RuntimeError("To restart, provide 'PSystem' and 'hdf5_file'")
+    assert suffix != "", "New HDF5 file name cannot coincide with previous run. Try changing 'suffix' name."
+    file_in = (in_path if in_path.endswith("/") else in_path + "/") + record_file
+    if record_file.endswith(".npz"):
+        z = np.load(file_in)
+        index, allbetas, chains = int(z["INDEX"][0]), z["BETAS"], z["CHAINS"]
+    else:
+        import h5py
+        with h5py.File(file_in, "r") as fh:
+            index, allbetas, chains = int(fh["INDEX"][0]), fh["BETAS"][...], fh["CHAINS"][...]
+    ladder = allbetas[0] if restart_ladder else allbetas[index]
+    print("\n =========== RESTARTING MCMC ===========\n")
+    print("--> Restarting from file: ", file_in)
+    print("--> Temperature ladder status: ", "Restarting temperature ladder" if restart_ladder
+          else "Temperature ladder continued")
+    print()
+    return {"p0": np.array(chains[:, :, index, :]), "betas": np.array(ladder), "itmax": itmax,
+            "intra_steps": intra_steps, "file_name": record_file.split(".")[-2], "path": out_path, "suffix": suffix}

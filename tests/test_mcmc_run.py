@@ -73,3 +73,24 @@ def test_argument_checks(oracle, tmp_path):
         nb.mcmc.run_mcmc(PS, p0, betas=[1.0, 0.5], sampler=mk(), save=False)
     with pytest.raises(RuntimeError, match="does not exist"):
         nb.mcmc.run_mcmc(PS, p0, sampler=mk(), path=str(tmp_path) + "/nowhere/")
+
+
+def test_restart_continues_from_the_last_saved_ensemble(oracle, tmp_path, capsys):
+    spec, PS, osys, p0, mk = _setup(oracle)
+    path = str(tmp_path) + "/"
+    s, rec = nb.mcmc.run_mcmc(PS, p0, itmax=9, intra_steps=3, tmax=20.0, sampler=mk(), path=path, file_name="first")
+    args = nb.mcmc.restart_mcmc(PS, "first.npz", in_path=path, out_path=str(tmp_path), itmax=6, intra_steps=2)
+    k = rec["INDEX"][0]
+    assert np.array_equal(args["p0"], rec["CHAINS"][:, :, k, :]) and np.array_equal(args["betas"], rec["BETAS"][k])
+    assert args["file_name"] == "first" and args["suffix"] == "_2" and args["path"] == path
+    again = nb.mcmc.restart_mcmc(PS, "first.npz", in_path=path, out_path=path, restart_ladder=True)
+    assert np.array_equal(again["betas"], rec["BETAS"][0])
+    smp = nb.mcmc.make_sampler(PS, args["p0"], betas=args["betas"], random=np.random.mtrand.RandomState(8),
+                               evaluate=lambda X: osys.loglike(X, mode=0)[1])
+    s2, rec2 = nb.mcmc.run_mcmc(PS, sampler=smp, **args)
+    assert os.path.exists(path + "first_2.npz") and rec2["ITER_LAST"][0] == 6 and np.array_equal(rec2["p0"], args["p0"])
+    with pytest.raises(AssertionError):
+        nb.mcmc.restart_mcmc(PS, "first.npz", in_path=path, out_path=path, suffix="")
+    with pytest.raises(RuntimeError, match="does not exists"):
+        nb.mcmc.restart_mcmc(PS, "first.npz", in_path=path, out_path=path + "nowhere")
+    capsys.readouterr()
