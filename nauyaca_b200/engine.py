@@ -61,6 +61,7 @@ class SpecSystem:
         self.sigma_obs = {p: dict(zip(o["epochs"], o["sigma"])) for p, o in spec["observed"].items()}
         self.second_term_logL = dict(spec.get("second_term_logL", {"sum": spec["second_term_sum"]}))
         self.params_names = spec.get("params_names", "")
+        self.params_names_all = spec.get("params_names_all", "")
 
 
 def _is_torch(x):

@@ -12,7 +12,7 @@ import numpy as np
 from . import utils as _u
 from .ptsampler import Sampler
 
-__all__ = ["make_sampler", "make_device_sampler", "pt_sample", "run_mcmc", "restart_mcmc", "write_hdf5"]
+__all__ = ["make_sampler", "make_device_sampler", "pt_sample", "run_mcmc", "restart_mcmc", "write_hdf5", "extract_best_solutions"]
 
 
 def _logprior_zero(x, psystem=None):
@@ -83,7 +83,7 @@ def _attr(PS, name, default):
 
 
 def run_mcmc(PSystem, p0, itmax=100, intra_steps=1, tmax=None, betas=None, seed=None, device=None, sampler=None,
-             path="./", file_name=None, suffix="", save=True, verbose=False, shard=False):
+             path="./", file_name=None, suffix="", save=True, verbose=False, shard=False, to_physical=None):
     """``MCMC.run`` (mcmc.py:141-312): ``itmax`` parallel-tempering iterations, the state looked
     at every ``intra_steps`` iterations. Returns ``(sampler, record)``; ``record`` holds what the
     reference stores in its HDF5 file, same names, shapes and meaning (mcmc.py:315-402):
@@ -94,8 +94,9 @@ def run_mcmc(PSystem, p0, itmax=100, intra_steps=1, tmax=None, betas=None, seed=
     sampler: default the device-resident sampler (``make_device_sampler``; its iterations between
     two looks run without any host round trip); a host ``Sampler`` (``make_sampler``, e.g. with a
     Python prior) is driven through ``sample(thin=intra_steps)`` exactly as the reference does.
-    save: write ``<path><file_name or system_name><suffix>.npz`` and, if h5py can be imported,
-    the same record as ``.hdf5`` in the reference's layout."""
+    save: write ``<path><file_name or system_name><suffix>.npz``, if h5py can be imported the same
+    record as ``.hdf5`` in the reference's layout, and the ``.best`` table of
+    ``extract_best_solutions``. to_physical: see ``extract_best_solutions``."""
     import os
     p0 = np.ascontiguousarray(p0, dtype=float)
     ntemps, nwalkers, ndim = p0.shape
@@ -186,6 +187,9 @@ def run_mcmc(PSystem, p0, itmax=100, intra_steps=1, tmax=None, betas=None, seed=
             pass
         else:
             rec["files"].append(write_hdf5(rec, base + ".hdf5"))
+        # mcmc.py:304-305: the best solutions of the run, in physical form, as a text table
+        extract_best_solutions(PSystem, rec, write_file=True, best_file=base + ".best", to_physical=to_physical)
+        rec["files"].append(base + ".best")
     return sampler, rec
 
 
@@ -245,3 +249,41 @@ def restart_mcmc(PSystem, record_file, in_path="./", out_path="./", itmax=100, i
     print()
     return {"p0": np.array(chains[:, :, index, :]), "betas": np.array(ladder), "itmax": itmax,
             "intra_steps": intra_steps, "file_name": record_file.split(".")[-2], "path": out_path, "suffix": suffix}
+
+
+def extract_best_solutions(PSystem, record, write_file=True, best_file=None, to_physical=None):
+    """``utils.extract_best_solutions`` (utils.py:874-934) for a ``run_mcmc`` record (the dict, or
+    the name of its ``.npz`` file): the saved best solution of every look, in physical form,
+    without repeated MAP values, best first; list of ``(MAP, physical vector)``. With
+    ``write_file`` the ``.best`` text table of the reference (header with Mstar, Rstar, Nplanets,
+    the parameter names, then one line per solution).
+    to_physical: X_cube[B, ndim] -> flat[B, 7*npla]; default the GPU engine of PSystem."""
+    from .optimizers import _writefile
+    name = None
+    if not isinstance(record, dict):
+        name = str(record)
+        record = np.load(name)
+    index = int(record["INDEX"][0])
+    cubes = np.asarray(record["BESTSOLS"][:index + 1], dtype=float)
+    if to_physical is None:
+        flat = _u.engine_for(PSystem).cube_to_physical(cubes)[0]
+    else:
+        flat = np.asarray(to_physical(cubes))
+    pairs = list(dict(zip([float(v) for v in record["MAP"][:index + 1]], list(flat))).items())
+    ranked = sorted(pairs, key=lambda t: t[0], reverse=True)
+    if write_file:
+        if best_file is None:
+            if name is None:
+                raise ValueError("best_file is needed when the record is not a file")
+            best_file = name.rsplit(".", 1)[0] + ".best"
+        names = getattr(PSystem, "params_names_all", "") or ""
+        _writefile(best_file, "w", "#Mstar[Msun]      Rstar[Rsun]     Nplanets", "%-10s " * 3 + "\n")
+        _writefile(best_file, "a", "#{}            {}           {}\n".format(record["MSTAR"][0], record["RSTAR"][0],
+                                                                             record["NPLA"][0]), "%-10s " * 3 + "\n")
+        head = "#MAP   " + names
+        _writefile(best_file, "a", head, "%-16s" + " %-11s" * (len(head.split()) - 1) + "\n")
+        for m, sol in ranked:
+            text = " " + str(m) + " " + " ".join(str(v) for v in sol)
+            _writefile(best_file, "a", text, "%-30s" + " %-11s" * (len(text.split()) - 1) + "\n")
+        print(f"--> Best solutions from the run will be written at: {best_file}")
+    return ranked

@@ -246,4 +246,10 @@ def test_run_mcmc_device_sampler(systems, known, spec_ps, oracle, tmp_path):
         state = ref.advance(4, adapt=True)
     assert np.all(rec["CHAINS"][:, :, 3, :] == 0)                      # the slot the reference leaves empty
     assert os.path.exists(str(tmp_path) + "/dev.npz")
+    # the .best table written at the end of the run (mcmc.py:304-305), physical vectors from the GPU
+    ranked = nb.mcmc.extract_best_solutions(PS, str(tmp_path) + "/dev.npz", write_file=False)
+    lines = open(str(tmp_path) + "/dev.best").read().splitlines()
+    assert len(lines) == 3 + len(ranked) and float(lines[3].split()[0]) == ranked[0][0] == rec["MAP"][:3].max()
+    k0 = int(np.flatnonzero(rec["MAP"][:3] == ranked[0][0])[-1])
+    assert list(ranked[0][1]) == list(osys.cube_to_physical(rec["BESTSOLS"][k0]))
     s.close(); ref.close()

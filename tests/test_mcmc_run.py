@@ -23,11 +23,12 @@ def _setup(oracle):
     return spec, PS, osys, p0, mk
 
 
-def test_record_follows_the_reference_loop(oracle, tmp_path):
+def test_record_follows_the_reference_loop(oracle, tmp_path, capsys):
     spec, PS, osys, p0, mk = _setup(oracle)
     itmax, intra = 13, 3
+    to_phys = lambda X: np.array([osys.cube_to_physical(x) for x in X])
     s, rec = nb.mcmc.run_mcmc(PS, p0, itmax=itmax, intra_steps=intra, tmax=20.0, sampler=mk(),
-                              path=str(tmp_path) + "/", file_name="run", suffix="_a")
+                              path=str(tmp_path) + "/", file_name="run", suffix="_a", to_physical=to_phys)
     nsteps = -(-itmax // intra)
     nlooks = itmax // intra
     assert rec["CHAINS"].shape == (3, 24, nsteps, spec["ndim"]) and rec["BETAS"].shape == (nsteps, 3)
@@ -61,9 +62,20 @@ def test_record_follows_the_reference_loop(oracle, tmp_path):
                 "p0", "BOUNDS", "NDIM", "NTEMPS", "NWALKERS", "ITMAX", "INTRA_STEPS", "REF_EPOCH", "NPLA", "MSTAR", "RSTAR"):
         assert np.array_equal(z[key], rec[key], equal_nan=True), key
     assert str(z["NAME"]) == rec["NAME"]
+    # the .best table (utils.py:874-934): best first, physical vectors of the saved solutions
+    ranked = nb.mcmc.extract_best_solutions(PS, str(tmp_path) + "/run_a.npz", write_file=False, to_physical=to_phys)
+    maps = [m for m, _ in ranked]
+    assert maps == sorted(set(rec["MAP"][:nlooks]), reverse=True)
+    k0 = int(np.flatnonzero(rec["MAP"][:nlooks] == maps[0])[-1])
+    assert np.array_equal(ranked[0][1], osys.cube_to_physical(rec["BESTSOLS"][k0]))
+    lines = open(str(tmp_path) + "/run_a.best").read().splitlines()
+    assert lines[0].split() == ["#Mstar[Msun]", "Rstar[Rsun]", "Nplanets"] and lines[2].startswith("#MAP")
+    assert len(lines) == 3 + len(ranked)
+    row = lines[3].split()
+    assert float(row[0]) == maps[0] and [float(v) for v in row[1:]] == list(ranked[0][1])
 
 
-def test_argument_checks(oracle, tmp_path):
+def test_argument_checks(oracle, tmp_path, capsys):
     spec, PS, osys, p0, mk = _setup(oracle)
     with pytest.raises(RuntimeError, match="nwalkers have to be >= 22"):
         nb.mcmc.run_mcmc(PS, p0[:, :20], sampler=mk(), save=False)
@@ -73,12 +85,15 @@ def test_argument_checks(oracle, tmp_path):
         nb.mcmc.run_mcmc(PS, p0, betas=[1.0, 0.5], sampler=mk(), save=False)
     with pytest.raises(RuntimeError, match="does not exist"):
         nb.mcmc.run_mcmc(PS, p0, sampler=mk(), path=str(tmp_path) + "/nowhere/")
+    capsys.readouterr()
 
 
 def test_restart_continues_from_the_last_saved_ensemble(oracle, tmp_path, capsys):
     spec, PS, osys, p0, mk = _setup(oracle)
     path = str(tmp_path) + "/"
-    s, rec = nb.mcmc.run_mcmc(PS, p0, itmax=9, intra_steps=3, tmax=20.0, sampler=mk(), path=path, file_name="first")
+    to_phys = lambda X: np.array([osys.cube_to_physical(x) for x in X])
+    s, rec = nb.mcmc.run_mcmc(PS, p0, itmax=9, intra_steps=3, tmax=20.0, sampler=mk(), path=path, file_name="first",
+                              to_physical=to_phys)
     args = nb.mcmc.restart_mcmc(PS, "first.npz", in_path=path, out_path=str(tmp_path), itmax=6, intra_steps=2)
     k = rec["INDEX"][0]
     assert np.array_equal(args["p0"], rec["CHAINS"][:, :, k, :]) and np.array_equal(args["betas"], rec["BETAS"][k])
@@ -87,7 +102,7 @@ def test_restart_continues_from_the_last_saved_ensemble(oracle, tmp_path, capsys
     assert np.array_equal(again["betas"], rec["BETAS"][0])
     smp = nb.mcmc.make_sampler(PS, args["p0"], betas=args["betas"], random=np.random.mtrand.RandomState(8),
                                evaluate=lambda X: osys.loglike(X, mode=0)[1])
-    s2, rec2 = nb.mcmc.run_mcmc(PS, sampler=smp, **args)
+    s2, rec2 = nb.mcmc.run_mcmc(PS, sampler=smp, to_physical=to_phys, **args)
     assert os.path.exists(path + "first_2.npz") and rec2["ITER_LAST"][0] == 6 and np.array_equal(rec2["p0"], args["p0"])
     with pytest.raises(AssertionError):
         nb.mcmc.restart_mcmc(PS, "first.npz", in_path=path, out_path=path, suffix="")
