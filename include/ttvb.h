@@ -93,7 +93,9 @@ int ttvb_device_count(void);
 /*
  * Upload the constants of one planetary system to `device` and allocate the handle's
  * workspaces. Replaces the per-call re-pickling of PSystem into the multiprocessing
- * workers (optimizers.py:185-189, mcmc.py:193-211).
+ * workers (optimizers.py:185-189, mcmc.py:193-211). TTVB_E_INVALID for inconsistent sizes,
+ * dt <= 0, non-finite times, mstar <= 0, sigma <= 0 or duplicate observed epochs;
+ * TTVB_E_UNSUPPORTED for more than TTVB_MAX_PLANETS planets; TTVB_E_NO_DEVICE without a GPU.
  */
 int ttvb_create(const ttvb_system *sys, int device, ttvb_handle **out);
 int ttvb_destroy(ttvb_handle *h);
