@@ -12,7 +12,10 @@
  *    error of the calling thread is available from ttvb_last_error(). Nothing throws or
  *    exits across this boundary.
  *  - a handle is bound to one CUDA device; calls on one handle are ordered on the stream
- *    given to the call (NULL = the legacy default stream). One handle per host thread.
+ *    given to the call (NULL = the legacy default stream). One handle per host thread. The
+ *    handle owns scratch state shared by all its launches, so launches of ONE handle never
+ *    overlap: a call given a different stream than the previous one first waits (on the device,
+ *    cudaStreamWaitEvent) for that previous launch. Use one handle per stream for concurrency.
  *  - `x`, and every output array, may be HOST or DEVICE pointers (detected with
  *    cudaPointerGetAttributes). With host buffers the call copies in chunks (cudaMemcpyAsync
  *    from/to the caller's buffers; pin them for full PCIe speed) through device staging owned
@@ -193,6 +196,16 @@ int ttvb_pt_get(ttvb_pt *pt, double *p, double *logl, double *betas, double *npr
  * Philox4x32-10 block for a counter/key, and the Feistel pairing permutation of {0..n-1}. */
 int ttvb_selftest_philox(const uint32_t counter[4], const uint32_t key[2], uint32_t out[4]);
 int ttvb_selftest_perm(uint32_t n, uint32_t k0, uint32_t k1, uint32_t *perm_out);
+
+/* Self-test of the reciprocal / reciprocal-square-root SEEDS the hot loop starts from
+ * (csrc/ttvb_math.cuh, "canonical arithmetic v3"): runs the table lookup that the CPU oracle and
+ * the host harness use (rcp_tab[2^20], rsq_tab[2^21] high words, host pointers; see
+ * oracle/mufu_sm100a.npz) on device `device` against the special-function unit for ALL 2^32 high
+ * operand words. mismatches[0/1] = number of high words where the rcp / rsqrt lookup differs from
+ * the hardware (NaN results compare as equal); first_bad[0..2] / [3..5] = (operand hi, hardware
+ * hi, lookup hi) of one offending word each, if any. */
+int ttvb_selftest_seed_scan(int device, const uint32_t *rcp_tab, const uint32_t *rsq_tab, uint64_t mismatches[2],
+                            uint32_t first_bad[6]);
 
 #ifdef __cplusplus
 }

@@ -31,7 +31,7 @@ EXPORTS = ["ttvb_last_error", "ttvb_version", "ttvb_device_count", "ttvb_create"
            "ttvb_set_cube_bounds", "ttvb_nsteps", "ttvb_loglike", "ttvb_ephemeris", "ttvb_cube_to_physical",
            "ttvb_last_kernel_ms", "ttvb_launch_count", "ttvb_fp64_peak",
            "ttvb_pt_create", "ttvb_pt_destroy", "ttvb_pt_set_walkers", "ttvb_pt_run", "ttvb_pt_get", "ttvb_pt_half_begin", "ttvb_pt_half_end", "ttvb_pt_proposal_logl",
-           "ttvb_selftest_philox", "ttvb_selftest_perm"]
+           "ttvb_selftest_philox", "ttvb_selftest_perm", "ttvb_selftest_seed_scan"]
 
 
 class TTVBError(RuntimeError):
@@ -123,6 +123,7 @@ def lib():
     L.ttvb_pt_half_end.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     L.ttvb_pt_proposal_logl.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.ttvb_fp64_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_float)]
+    L.ttvb_selftest_seed_scan.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     _lib = L
     return L
 

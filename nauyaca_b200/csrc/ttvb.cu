@@ -63,6 +63,7 @@ struct ttvb_handle {
     size_t ctx_bytes = 0;
     int force_nseg = 0;          // TTVB_NSEG (0 = choose per launch)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev_done = nullptr;   // end of the last launch that used the handle's scratch state
     bool timed = false;
     long long launches = 0;
 };
@@ -327,7 +328,8 @@ int ttvb_create(const ttvb_system* sys, int device, ttvb_handle** out) {
     if (cudaMalloc(&h->d_queue, qbytes) != cudaSuccess) return bail(fail(TTVB_E_CUDA, "cudaMalloc(event queues, %zu B) failed", qbytes));
     S.queue = h->d_queue; S.queue_stride = h->queue_stride;
 
-    if (cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess)
+    if (cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming) != cudaSuccess)
         return bail(fail(TTVB_E_CUDA, "cudaEventCreate failed"));
     *out = h;
     return TTVB_OK;
@@ -346,6 +348,7 @@ int ttvb_destroy(ttvb_handle* h) {
 
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->ev_done) cudaEventDestroy(h->ev_done);
     delete h;
     return TTVB_OK;
 }
@@ -388,6 +391,10 @@ static int run_batch(ttvb_handle* h, const double* x, int64_t B, int mode, doubl
     const int rowlen = S.rowlen, N = h->npla;
     S.cap = cap;
     h->timed = false;
+    // The handle's scratch state (unit counter and segment flags, event queues, hand-over
+    // context, staging) is shared by all its launches: a call on another stream first waits for
+    // the previous launch of this handle, so two streams can never run on it at the same time.
+    CU(cudaStreamWaitEvent(st, h->ev_done, 0));
 
     if (dev) {
         S.B = B; S.x = x;
@@ -401,12 +408,18 @@ static int run_batch(ttvb_handle* h, const double* x, int64_t B, int mode, doubl
         rc = dispatch_launch(h, S, grid, st);
         if (rc != TTVB_OK) return rc;
         CU(cudaEventRecord(h->ev1, st));
+        CU(cudaEventRecord(h->ev_done, st));
         h->timed = true;
         return TTVB_OK;
     }
 
     // host pointers: chunked H2D -> kernel -> D2H on `st`, then synchronise
-    const long long chunk = std::min<long long>(B, CHUNK);
+    long long chunk = std::min<long long>(B, CHUNK);
+    if (table) {
+        // an event table needs cap*28 bytes per system: bound the staging of one chunk to ~1 GiB
+        const size_t per_sys = (size_t)cap * 32 + (size_t)rowlen * 8 + 64;
+        chunk = std::max<long long>(1, std::min<long long>(chunk, (long long)(((size_t)1 << 30) / per_sys)));
+    }
     size_t off_x = 0, bytes = align256((size_t)chunk * rowlen * 8);
     size_t off_chi2 = bytes; bytes += align256((size_t)chunk * 8);
     size_t off_logl = bytes; bytes += align256((size_t)chunk * 8);
@@ -459,6 +472,7 @@ static int run_batch(ttvb_handle* h, const double* x, int64_t B, int mode, doubl
         }
     }
     CU(cudaEventRecord(h->ev1, st));
+    CU(cudaEventRecord(h->ev_done, st));
     h->timed = true;
     CU(cudaStreamSynchronize(st));
     return TTVB_OK;
@@ -716,6 +730,31 @@ int ttvb_selftest_perm(uint32_t n, uint32_t k0, uint32_t k1, uint32_t* perm_out)
     while ((1u << bits) < n) bits++;
     const int hb = (bits + 1) / 2;
     for (uint32_t w = 0; w < n; w++) perm_out[w] = ttvb::feistel_perm(w, n, hb, k0, k1);
+    return TTVB_OK;
+}
+
+int ttvb_selftest_seed_scan(int device, const uint32_t* rcp_tab, const uint32_t* rsq_tab, uint64_t mismatches[2],
+                            uint32_t first_bad[6]) {
+    if (!rcp_tab || !rsq_tab || !mismatches || !first_bad) return fail(TTVB_E_INVALID, "null argument");
+    int ndev = ttvb_device_count();
+    if (ndev <= 0) return fail(TTVB_E_NO_DEVICE, "no CUDA device available (libttvb has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(TTVB_E_NO_DEVICE, "device %d out of range (0..%d)", device, ndev - 1);
+    CU(cudaSetDevice(device));
+    uint32_t *d_rcp = nullptr, *d_rsq = nullptr, *d_first = nullptr;
+    unsigned long long* d_bad = nullptr;
+    CU(cudaMalloc(&d_rcp, 4u << 20)); CU(cudaMalloc(&d_rsq, 8u << 20));
+    CU(cudaMalloc(&d_bad, 16)); CU(cudaMalloc(&d_first, 24));
+    CU(cudaMemcpy(d_rcp, rcp_tab, 4u << 20, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_rsq, rsq_tab, 8u << 20, cudaMemcpyHostToDevice));
+    CU(cudaMemset(d_bad, 0, 16)); CU(cudaMemset(d_first, 0, 24));
+    ttvb::ttvb_seed_scan_kernel<<<148 * 16, 256>>>(d_rcp, d_rsq, d_bad, d_first);
+    CU(cudaGetLastError());
+    CU(cudaDeviceSynchronize());
+    unsigned long long bad[2];
+    CU(cudaMemcpy(bad, d_bad, 16, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(first_bad, d_first, 24, cudaMemcpyDeviceToHost));
+    mismatches[0] = bad[0]; mismatches[1] = bad[1];
+    cudaFree(d_rcp); cudaFree(d_rsq); cudaFree(d_bad); cudaFree(d_first);
     return TTVB_OK;
 }
 

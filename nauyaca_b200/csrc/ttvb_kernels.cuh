@@ -800,6 +800,26 @@ __global__ void ttvb_cube_to_physical_kernel(const __grid_constant__ DevSys S, d
     }
 }
 
+// Seed self-test: the table lookup of ttvb_math.cuh (what the CPU oracle uses) against the
+// special-function unit, for every high operand word. A NaN on both sides counts as equal.
+__global__ void ttvb_seed_scan_kernel(const uint32_t* rcp_tab, const uint32_t* rsq_tab, unsigned long long* bad,
+                                      uint32_t* first_bad) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; w < (1ull << 32); w += stride) {
+        const uint32_t hi = (uint32_t)w;
+        const double x = __hiloint2double((int)hi, (int)(hi * 2654435761u));
+        const uint32_t hr = (uint32_t)__double2hiint(rcp_seed(x)), hs = (uint32_t)__double2hiint(rsq_seed(x));
+        const uint32_t er = seed_rcp_emul(hi, rcp_tab), es = seed_rsq_emul(hi, rsq_tab);
+        auto is_nan = [](uint32_t h) { return (h & 0x7FF00000u) == 0x7FF00000u && (h & 0xFFFFFu) != 0u; };
+        if (hr != er && !(is_nan(hr) && is_nan(er))) {
+            if (atomicAdd(bad, 1ull) == 0ull) { first_bad[0] = hi; first_bad[1] = hr; first_bad[2] = er; }
+        }
+        if (hs != es && !(is_nan(hs) && is_nan(es))) {
+            if (atomicAdd(bad + 1, 1ull) == 0ull) { first_bad[3] = hi; first_bad[4] = hs; first_bad[5] = es; }
+        }
+    }
+}
+
 // FP64 FMA-chain microbenchmark: 8 independent chains per thread
 __global__ void ttvb_fp64_peak_kernel(double* out, int iters, double a, double b) {
     double c0 = threadIdx.x, c1 = c0 + 1, c2 = c0 + 2, c3 = c0 + 3, c4 = c0 + 4, c5 = c0 + 5, c6 = c0 + 6, c7 = c0 + 7;

@@ -146,6 +146,8 @@ class BatchEngine:
                 raise TTVBError("torch input must be a CUDA tensor (use numpy for host buffers)")
             if X.dtype != torch.float64 or not X.is_contiguous() or X.dim() != 2 or X.shape[1] != self.rowlen(mode):
                 raise ValueError("X must be a contiguous float64 CUDA tensor [B, rowlen]")
+            if X.device.index != self.device:
+                raise ValueError(f"X lives on cuda:{X.device.index}, the engine on cuda:{self.device}")
             B = X.shape[0]
             chi2 = torch.empty(B, dtype=torch.float64, device=X.device)
             logl = torch.empty(B, dtype=torch.float64, device=X.device)
@@ -165,7 +167,8 @@ class BatchEngine:
         return (chi2, logl, st, pl) if per_planet else (chi2, logl, st)
 
     def loglike_into(self, x_ptr, B, mode, chi2_ptr, logl_ptr, status_ptr, stream=None):
-        """Raw-pointer form (host or device pointers, caller-owned buffers)."""
+        """Raw-pointer form (host or device pointers, caller-owned buffers). Device pointers must
+        belong to the engine's device (self.device): the kernel is launched there."""
         _lib.check(_lib.lib().ttvb_loglike(self._h, x_ptr, B, mode, chi2_ptr, logl_ptr, None, status_ptr,
                                            C.c_void_p(stream) if stream else None))
 

@@ -399,8 +399,21 @@ class DeviceSampler:
             raise ValueError('The number of walkers must be even.')
         if self.nwalkers < 2 * self.dim:
             raise ValueError('The number of walkers must be greater than ``2*dimension``.')
+        self._world, self._rank, self._group = 1, 0, group
+        if shard:
+            import torch.distributed as dist
+            if dist.is_initialized():
+                self._world, self._rank = dist.get_world_size(group), dist.get_rank(group)
         if seed is None:
             seed = int(np.random.SeedSequence().generate_state(2, dtype=np.uint32).view(np.uint64)[0])
+            if self._world > 1:
+                # every rank must make the same moves: rank 0 draws the seed for all of them
+                box = [seed]
+                dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0,
+                                           group=group)
+                seed = int(box[0])
+        elif self._world > 1:
+            self._same_on_all_ranks(int(seed), "seed")
         self._pt = C.c_void_p()
         _lib.check(_lib.lib().ttvb_pt_create(engine._h, self.ntemps, self.nwalkers, self._betas.ctypes.data, float(a),
                                              float(adaptation_lag), float(adaptation_time), C.c_uint64(seed),
@@ -408,17 +421,19 @@ class DeviceSampler:
         self._time = 0
         self._started = False
         self._chain = self._logposterior = self._loglikelihood = self._beta_history = None
-        self._world, self._rank, self._group = 1, 0, group
-        if shard:
-            import torch.distributed as dist
-            if dist.is_initialized():
-                self._world, self._rank = dist.get_world_size(group), dist.get_rank(group)
-            if self._world > 1 and seed is None:
-                raise ValueError('a sharded DeviceSampler needs the same explicit seed on every rank')
         shape = (self.ntemps, self.nwalkers)
         self._p = np.empty(shape + (self.dim,)); self._logl = np.empty(shape)
         self.nprop = np.zeros(shape); self.nprop_accepted = np.zeros(shape)
         self.nswap = np.zeros(self.ntemps); self.nswap_accepted = np.zeros(self.ntemps)
+
+    def _same_on_all_ranks(self, value, what):
+        """A sharded run is only right if every rank holds the same ensemble: compare a value (or a
+        digest) across the ranks of the group and raise on all of them if it differs."""
+        import torch.distributed as dist
+        got = [None] * self._world
+        dist.all_gather_object(got, value, group=self._group)
+        if any(g != got[0] for g in got):
+            raise ValueError(f'sharded DeviceSampler: {what} differs between ranks: {got}')
 
     def close(self):
         if getattr(self, "_pt", None) is not None and self._pt.value:
@@ -446,6 +461,9 @@ class DeviceSampler:
             p0 = np.ascontiguousarray(p0, dtype=np.float64)
             if p0.shape != (self.ntemps, self.nwalkers, self.dim):
                 raise ValueError('p0 must have shape (ntemps, nwalkers, dim).')
+            if self._world > 1:
+                import hashlib
+                self._same_on_all_ranks(hashlib.sha1(p0.tobytes()).hexdigest(), "p0")
             self._lib.check(L.ttvb_pt_set_walkers(self._pt, p0.ctypes.data, None))
             self._started = True
             p, logpost, logl = self._fetch()

@@ -46,7 +46,31 @@ def lib():
         _lib.ttvo_chi2.restype = C.c_double
         _lib.ttvo_test_cbrt.restype = C.c_double
         _lib.ttvo_test_cbrt.argtypes = [C.c_double]
+        rcp, rsq = seed_tables()
+        _lib.ttvo_set_seed_tables(_p(rcp), _p(rsq))
     return _lib
+
+
+_TABLES = None
+
+
+def seed_tables():
+    """High words of the sm_100a FP64 reciprocal / reciprocal-square-root seeds (MUFU.RCP64H over
+    operands 1.m, MUFU.RSQ64H over 1.m and 2*1.m; m = 20 mantissa bits), stored as deltas in
+    oracle/mufu_sm100a.npz (dumped by scripts/mufu_dump.cu; the sha256 of the raw tables is in
+    the file). Returns (rcp[2^20], rsq[2^21]) uint32; the arrays stay alive for the C side."""
+    global _TABLES
+    if _TABLES is None:
+        import hashlib
+        z = np.load(os.path.join(_HERE, "mufu_sm100a.npz"))
+        out = []
+        for k in ("rcp", "rsq"):
+            first = np.int64(z[k + "_first"])
+            t = np.concatenate([[first], first + np.cumsum(z[k + "_delta"].astype(np.int64))]).astype(np.uint32)
+            out.append(np.ascontiguousarray(t))
+        assert [hashlib.sha256(t.tobytes()).hexdigest() for t in out] == list(z["sha256"])
+        _TABLES = tuple(out)
+    return _TABLES
 
 
 def _p(a):

@@ -70,6 +70,9 @@ def harness():
     if (not os.path.exists(so)) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
         subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-mfma", "-fPIC", "-shared", "-o", so, src])
     lib = C.CDLL(so)
+    from oracle import oracle_py
+    rcp, rsq = oracle_py.seed_tables()
+    lib.hh_set_seed_tables(rcp.ctypes.data_as(C.c_void_p), rsq.ctypes.data_as(C.c_void_p))
 
     def eph(flat, mstar, t0, dt, total, cap=5000):
         flat = np.ascontiguousarray(flat, np.float64)

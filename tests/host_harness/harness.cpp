@@ -101,6 +101,12 @@ static int run(const double* flat, double mstar, double t0, double dt, double to
     return status;
 }
 
+// the seed tables of oracle/mufu_sm100a.npz (see ttvb_math.cuh, "canonical arithmetic v3")
+extern "C" void hh_set_seed_tables(const uint32_t* rcp, const uint32_t* rsq) {
+    host_seed_tables().rcp = rcp;
+    host_seed_tables().rsq = rsq;
+}
+
 extern "C" int hh_ephemeris(const double* flat, int npla, double mstar, double t0, double dt, double total, int cap,
                             int* n_events, int* planet, int* epoch, double* time, double* rsky, double* vsky) {
     switch (npla) {

@@ -202,6 +202,25 @@ def test_device_sampler_sharded(systems, known, spec_ps, tmp_path):
         z = np.load(tmp_path / f"r{r}.npz")
         assert np.array_equal(z["p"], p) and np.array_equal(z["logl"], logl)
         assert np.array_equal(z["betas"], one.betas) and np.array_equal(z["nacc"], one.nprop_accepted)
+    # without a seed: rank 0 draws one and broadcasts it, so both ranks still hold ONE ensemble
+    procs = [subprocess.Popen([sys.executable, worker, str(r), "2", str(int(port) + 1), str(tmp_path / f"u{r}.npz"),
+                               str(tmp_path / "p0.npy"), "gloo", "none"]) for r in range(2)]
+    for pr in procs:
+        assert pr.wait(timeout=300) == 0
+    u0, u1 = np.load(tmp_path / "u0.npz"), np.load(tmp_path / "u1.npz")
+    assert np.array_equal(u0["p"], u1["p"]) and np.array_equal(u0["logl"], u1["logl"])
+    assert np.isfinite(u0["logl"]).all() and not np.array_equal(u0["p"], p)
+    # NCCL path (one GPU per rank, in-place all-gather of the proposal log-likelihoods on the
+    # device buffer): needs two GPUs
+    if nb._lib.lib().ttvb_device_count() >= 2:
+        procs = [subprocess.Popen([sys.executable, worker, str(r), "2", str(int(port) + 2), str(tmp_path / f"n{r}.npz"),
+                                   str(tmp_path / "p0.npy"), "nccl"]) for r in range(2)]
+        for pr in procs:
+            assert pr.wait(timeout=300) == 0
+        for r in range(2):
+            z = np.load(tmp_path / f"n{r}.npz")
+            assert np.array_equal(z["p"], p) and np.array_equal(z["logl"], logl)
+            assert np.array_equal(z["betas"], one.betas) and np.array_equal(z["nacc"], one.nprop_accepted)
     one.close()
 
 
