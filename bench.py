@@ -136,18 +136,20 @@ def make_workload(name, engine_factory):
 def _cpu_worker(args):
     spec, X = args
     from oracle import oracle_py
-    osys = oracle_py.OracleSystem(spec)
+    osys = oracle_py.OracleSystem(spec, native=True)
     t = time.perf_counter()
     chi2, logl, st = osys.loglike(X, mode=0)
     return time.perf_counter() - t, float(np.sum(logl[np.isfinite(logl)]))
 
 
 def cpu_rate(spec, X, budget_s, cores):
-    """Oracle port over `cores` processes on a bounded sample; returns (evals/s, n_sample)."""
+    """Oracle port over `cores` processes on a bounded sample; returns (evals/s, n_sample). Timed
+    on the oracle's NATIVE build (the host's own divide and square root): the checker build emulates
+    the GPU's reciprocal seeds by table look-up, which would cost a CPU four times the arithmetic."""
     import multiprocessing as mp
     from oracle import oracle_py
     oracle_py.build()
-    osys = oracle_py.OracleSystem(spec)
+    osys = oracle_py.OracleSystem(spec, native=True)
     t = time.perf_counter()
     osys.loglike(X[:4], mode=0)
     per = max((time.perf_counter() - t) / 4, 1e-5)
@@ -161,6 +163,50 @@ def cpu_rate(spec, X, budget_s, cores):
         pool.map(_cpu_worker, [(spec, c) for c in chunks])
         wall = time.perf_counter() - t
     return n / wall, n
+
+
+_PLUMB = {}
+
+
+def _plumb_init(base, spec):
+    import contextlib
+    import io
+    os.environ["TTVO_NATIVE"] = "1"
+    from oracle import ref_plumbing, ref_systems
+    with contextlib.redirect_stdout(io.StringIO()):
+        nau, U = ref_plumbing.import_reference()
+        PS = ref_systems.with_spec(ref_systems.build(nau, ref_plumbing.inputs_dir())[base], spec)
+    _PLUMB["f"], _PLUMB["PS"] = U.log_likelihood_func, PS
+
+
+def _plumb_work(x):
+    return _PLUMB["f"](x, _PLUMB["PS"])
+
+
+def plumbing_rate(workload, spec, X, budget_s, cores):
+    """the UNMODIFIED reference Python path (nauyaca.utils.log_likelihood_func,
+    utils.py:333-399, from baseline/_ref) under multiprocessing.Pool(cores).map, as mcmc.py:193
+    runs it, with the oracle port (native build) standing in for the ttvfast C extension, which
+    cannot be installed here. Returns None where the reference package is absent."""
+    import multiprocessing as mp
+    from oracle import ref_plumbing
+    if ref_plumbing.reference_dir() is None:
+        return None
+    base = {"c2": "doc2", "c3": "doc2", "c5": "sys3", "c4": "sys3f"}[workload]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores, initializer=_plumb_init, initargs=(base, spec)) as pool:
+        pool.map(_plumb_work, list(X[:2 * cores]))                            # warm-up (imports, first calls)
+        t = time.perf_counter()
+        pool.map(_plumb_work, list(X[:2 * cores]))                            # rate estimate
+        per = max((time.perf_counter() - t) / 2, 1e-4)                        # seconds per call per core
+        n = int(max(cores, min(X.shape[0], cores * budget_s / per)))
+        t = time.perf_counter()
+        vals = pool.map(_plumb_work, list(X[:n]))
+        wall = time.perf_counter() - t
+    return {"value": n / wall, "unit": "evals/s", "cores": cores, "kind": "reference-plumbing",
+            "sample": f"first {n} walkers, nauyaca.utils.log_likelihood_func (unmodified, baseline/_ref) under "
+                      f"multiprocessing.Pool({cores}).map over an oracle-backed ttvfast module",
+            "finite": int(np.isfinite(vals).sum())}
 
 
 def run_reference(args):
@@ -191,8 +237,12 @@ def run_reference(args):
            "dtype": "f64", "data": "synthetic",
            "config": {"workload": desc},
            "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "port",
-                            "sample": f"{n} walkers of the workload per step, oracle C port in {cores} processes"},
+                            "sample": f"{n} walkers of the workload per step, oracle C port (native divide/sqrt build) in {cores} processes"},
            "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if not args.no_plumbing:
+        pl = plumbing_rate(args.workload, spec, X, 8.0, cores)
+        if pl is not None:
+            out["cpu_baseline"]["plumbing"] = pl
     print(json.dumps(out))
 
 
@@ -410,7 +460,11 @@ def run_gpu(args):
             cores = os.cpu_count() or 1
             rate, n = cpu_rate(spec, X, 12.0, cores)
             out["cpu_baseline"] = {"value": rate, "unit": "evals/s", "cores": cores, "kind": "port",
-                                   "sample": f"first {n} walkers of the same batch, oracle C port in {cores} processes"}
+                                   "sample": f"first {n} walkers of the same batch, oracle C port (native divide/sqrt build) in {cores} processes"}
+            if not args.no_plumbing:
+                pl = plumbing_rate(args.workload, spec, X, 8.0, cores)
+                if pl is not None:
+                    out["cpu_baseline"]["plumbing"] = pl
         print(json.dumps(out))
     eng.close()
     if world > 1:
@@ -506,6 +560,108 @@ def run_c3(args):
         dist.barrier(); dist.destroy_process_group()
 
 
+def run_c5_strong(args):
+    """BASELINE configs[4] as a STRONG-scaling job: the 10^7-point uniform sweep of the 3-planet
+    system (init_walkers / parameter-grid shape, utils.py:463-543), fixed total, split into
+    contiguous shards over the ranks. A step = the whole sweep, end to end: every rank streams
+    its shard from PINNED HOST memory through the C ABI (chunked, uploads and downloads under
+    the kernels), log-likelihoods come back to the host, and ONE all-gather at the end gives every
+    rank all 10^7 values (the sweep's only exchange). value == e2e by construction."""
+    from nauyaca_b200 import _lib as _ttvb_lib
+    _ttvb_lib.ensure_built(builder=int(os.environ.get("LOCAL_RANK", "0")) == 0)
+    import torch
+    import nauyaca_b200 as nb
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    spec = dict(load_systems()["sys3"])
+    total = int(args.sweep_points)
+    lo, hi = nb.shard_bounds(total, world, rank)
+    B, ndim = hi - lo, spec["ndim"]
+    # row i of the sweep is the same whatever the number of ranks: blocks of 10^6 rows, one seed each
+    BLK = 1_000_000
+    Xh = torch.empty((B, ndim), dtype=torch.float64).pin_memory()
+    Xn = Xh.numpy()
+    for blk in range(lo // BLK, (hi - 1) // BLK + 1):
+        rows = np.random.default_rng([SEED, blk]).random((min(BLK, total - blk * BLK), ndim))
+        a, b = max(lo, blk * BLK), min(hi, (blk + 1) * BLK)
+        Xn[a - lo:b - lo] = rows[a - blk * BLK:b - blk * BLK]
+    logl_h = torch.empty(B, dtype=torch.float64).pin_memory()
+    stat_h = torch.empty(B, dtype=torch.int32).pin_memory()
+    eng = nb.BatchEngine(spec, device=local)
+    stream = torch.cuda.current_stream().cuda_stream
+    maxb = nb.shard_bounds(total, world, 0)[1]
+    mine = torch.zeros(maxb, dtype=torch.float64, device="cuda")
+    gathered = torch.empty(world * maxb, dtype=torch.float64, device="cuda") if world > 1 else None
+
+    def sweep():
+        eng.loglike_into(Xh.data_ptr(), B, nb.MODE_CUBE, None, logl_h.data_ptr(), stat_h.data_ptr(), stream)
+        if world > 1:
+            mine[:B].copy_(logl_h, non_blocking=True)
+            dist.all_gather_into_tensor(gathered, mine)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        sweep()
+    sync_all()
+    clocks = ClockSampler(local); clocks.start()
+    l0 = eng.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        sweep()
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    launches = eng.launch_count() - l0
+    clk = clocks.stop()
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    # what the kernels alone take on this rank's shard (resident input), for the roofline line
+    Xd = torch.from_numpy(Xn[:min(B, 1_000_000)]).cuda()
+    o1 = torch.empty(Xd.shape[0], dtype=torch.float64, device="cuda"); o2 = torch.empty_like(o1)
+    o3 = torch.empty(Xd.shape[0], dtype=torch.int32, device="cuda")
+    eng.loglike_into(Xd.data_ptr(), Xd.shape[0], nb.MODE_CUBE, o1.data_ptr(), o2.data_ptr(), o3.data_ptr(), stream)
+    torch.cuda.synchronize()
+    kms = eng.last_kernel_ms()
+    if rank == 0:
+        value = total * args.steps / (ms * 1e-3)
+        n_ev, *_ = eng.ephemeris(eng.cube_to_physical(Xn[:256])[0], mode=2, cap=1024)
+        f_eval = flops_per_eval(spec["npla"], eng.nsteps, float(np.mean(n_ev)))
+        peak = eng.fp64_peak_tflops()
+        achieved = f_eval * Xd.shape[0] / (kms * 1e-3) / 1e12
+        out = {"metric": "likelihood evals/sec", "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
+               "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+               "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": {"workload": f"C5 sweep: 3-planet system (500 d, dt 0.34874, 1434 steps, 105 obs), {total} U(0,1) points "
+                                      f"in total, contiguous shards over {world} GPU(s), host buffers in and out, one "
+                                      "all_gather(logl) at the end of the sweep",
+                          "points_total": total, "points_per_gpu": B, "ndim": ndim, "npla": spec["npla"], "nsteps": eng.nsteps,
+                          "l2": "inputs (1.44 GB in total) far larger than L2",
+                          "collective": "all_gather(logl) once per sweep" if world > 1 else "none"},
+               "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": int(B * ndim * 8),
+                       "d2h_bytes_per_step": int(B * 12)},
+               "gpu_launches": int(launches), "clocks": clk,
+               "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                            "traffic": None, "kernel_ms": kms, "kernel_batch": int(Xd.shape[0]), "flop_per_eval": f_eval,
+                            "note": "kernel alone on a resident chunk of this rank's shard"}}
+        print(json.dumps(out))
+    eng.close()
+    if world > 1:
+        dist.barrier(); dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -515,13 +671,20 @@ def main():
     ap.add_argument("--workload", default="c4", choices=["c2", "c3", "c4", "c5"])
     ap.add_argument("--per-kernel", action="store_true", help="read the kernel time after every step (adds a sync)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-plumbing", action="store_true",
+                    help="skip the reference-plumbing CPU leg (unmodified nauyaca.utils under multiprocessing)")
     ap.add_argument("--host-sampler", action="store_true", help="c3: sampler moves in numpy on the host instead of on the device")
     ap.add_argument("--shard-walkers", action="store_true",
                     help="c3 with N > 1: ONE ensemble, the proposals of every half-step sharded over the GPUs and their "
                          "log-likelihoods all-gathered over NCCL (strong scaling) instead of one replica per GPU")
+    ap.add_argument("--strong", action="store_true",
+                    help="c5: the fixed 10^7-point sweep split over the GPUs (strong scaling, host buffers, one gather)")
+    ap.add_argument("--sweep-points", type=int, default=10_000_000, help="c5 --strong: total points of the sweep")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "c5" and args.strong:
+        run_c5_strong(args)
     elif args.workload == "c3":
         run_c3(args)
     else:

@@ -64,6 +64,9 @@ struct ttvb_handle {
     int force_nseg = 0;          // TTVB_NSEG (0 = choose per launch)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t ev_done = nullptr;   // end of the last launch that used the handle's scratch state
+    // host-pointer calls: copy-in / copy-out streams and the events of the two staging buffers
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_krn[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     bool timed = false;
     long long launches = 0;
 };
@@ -193,6 +196,18 @@ int ensure_stage(ttvb_handle* h, size_t bytes) {
     if (h->d_stage) { CU(cudaFree(h->d_stage)); h->d_stage = nullptr; h->stage_bytes = 0; }
     CU(cudaMalloc(&h->d_stage, bytes));
     h->stage_bytes = bytes;
+    return TTVB_OK;
+}
+
+int ensure_copy_streams(ttvb_handle* h) {
+    if (h->s_in) return TTVB_OK;
+    CU(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        CU(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&h->ev_krn[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming));
+    }
     return TTVB_OK;
 }
 
@@ -349,6 +364,13 @@ int ttvb_destroy(ttvb_handle* h) {
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev_done) cudaEventDestroy(h->ev_done);
+    for (int i = 0; i < 2; i++) {
+        if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
+        if (h->ev_krn[i]) cudaEventDestroy(h->ev_krn[i]);
+        if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]);
+    }
+    if (h->s_in) cudaStreamDestroy(h->s_in);
+    if (h->s_out) cudaStreamDestroy(h->s_out);
     delete h;
     return TTVB_OK;
 }
@@ -413,13 +435,34 @@ static int run_batch(ttvb_handle* h, const double* x, int64_t B, int mode, doubl
         return TTVB_OK;
     }
 
-    // host pointers: chunked H2D -> kernel -> D2H on `st`, then synchronise
-    long long chunk = std::min<long long>(B, CHUNK);
+    // host pointers: the batch is cut into chunks that flow through TWO staging buffers, so that
+    // the upload of chunk k+1 (copy-in stream) and the download of chunk k-1 (copy-out stream)
+    // run under the kernel of chunk k (caller's stream). The kernels themselves stay in order on
+    // `st` (they share the handle's scheduling state). Returns after the results are on the host.
+    // Chunk schedule: whole waves (one wave = as many systems as the resident CTAs hold, so a chunk
+    // leaves no partly filled round behind), the first chunk ONE wave so that only a small upload is
+    // exposed before the first kernel starts, then doubling up to ~2^20 systems.
+    const long long wave = (long long)h->max_grid * h->tpb;
+    long long cap_sys = std::max<long long>(wave, (CHUNK / wave) * wave);
     if (table) {
-        // an event table needs cap*28 bytes per system: bound the staging of one chunk to ~1 GiB
+        // an event table needs cap*28 bytes per system: bound the staging of one chunk to ~0.5 GiB
         const size_t per_sys = (size_t)cap * 32 + (size_t)rowlen * 8 + 64;
-        chunk = std::max<long long>(1, std::min<long long>(chunk, (long long)(((size_t)1 << 30) / per_sys)));
+        cap_sys = std::max<long long>(1, std::min<long long>(cap_sys, (long long)(((size_t)1 << 29) / per_sys)));
     }
+    std::vector<long long> starts, sizes;
+    {
+        long long b0 = 0, next = std::min<long long>(wave, cap_sys);
+        while (b0 < B) {
+            long long nb = std::min<long long>(next, B - b0);
+            const long long rem = B - b0 - nb;
+            if (!table && rem > 0 && rem < wave / 2) nb += rem;          // no tiny last chunk
+            starts.push_back(b0); sizes.push_back(nb);
+            b0 += nb;
+            next = std::min<long long>(cap_sys, next * 2);
+        }
+    }
+    long long chunk = 0;
+    for (long long v : sizes) chunk = std::max(chunk, v);
     size_t off_x = 0, bytes = align256((size_t)chunk * rowlen * 8);
     size_t off_chi2 = bytes; bytes += align256((size_t)chunk * 8);
     size_t off_logl = bytes; bytes += align256((size_t)chunk * 8);
@@ -434,13 +477,28 @@ static int run_batch(ttvb_handle* h, const double* x, int64_t B, int mode, doubl
         off_er = bytes;  bytes += align256((size_t)chunk * cap * 8);
         off_ev = bytes;  bytes += align256((size_t)chunk * cap * 8);
     }
-    int rc = ensure_stage(h, bytes);
+    const long long nchunks = (long long)sizes.size();
+    const int nbuf = nchunks > 1 ? 2 : 1;
+    int rc = ensure_stage(h, bytes * nbuf);
     if (rc != TTVB_OK) return rc;
-    unsigned char* d = h->d_stage;
+    rc = ensure_copy_streams(h);
+    if (rc != TTVB_OK) return rc;
     CU(cudaEventRecord(h->ev0, st));
-    for (long long b0 = 0; b0 < B; b0 += chunk) {
-        const long long nb = std::min<long long>(chunk, B - b0);
-        CU(cudaMemcpyAsync(d + off_x, x + b0 * rowlen, (size_t)nb * rowlen * 8, cudaMemcpyHostToDevice, st));
+    auto upload = [&](long long k) -> int {
+        const int bf = (int)(k % nbuf);
+        const long long b0 = starts[k], nb = sizes[k];
+        unsigned char* d = h->d_stage + (size_t)bf * bytes;
+        if (k >= nbuf) CU(cudaStreamWaitEvent(h->s_in, h->ev_out[bf], 0));      // buffer free again (chunk k-2 downloaded)
+        CU(cudaMemcpyAsync(d + off_x, x + b0 * rowlen, (size_t)nb * rowlen * 8, cudaMemcpyHostToDevice, h->s_in));
+        CU(cudaEventRecord(h->ev_in[bf], h->s_in));
+        return TTVB_OK;
+    };
+    rc = upload(0);
+    if (rc != TTVB_OK) return rc;
+    for (long long k = 0; k < nchunks; k++) {
+        const int bf = (int)(k % nbuf);
+        const long long b0 = starts[k], nb = sizes[k];
+        unsigned char* d = h->d_stage + (size_t)bf * bytes;
         S.B = nb; S.x = (const double*)(d + off_x);
         S.chi2_out = chi2_out ? (double*)(d + off_chi2) : nullptr;
         S.logl_out = logl_out ? (double*)(d + off_logl) : nullptr;
@@ -453,24 +511,32 @@ static int run_batch(ttvb_handle* h, const double* x, int64_t B, int mode, doubl
             S.n_events = nullptr; S.ev_planet = nullptr; S.ev_epoch = nullptr;
             S.ev_time = nullptr; S.ev_rsky = nullptr; S.ev_vsky = nullptr;
         }
+        CU(cudaStreamWaitEvent(st, h->ev_in[bf], 0));
         int grid = 0;
         rc = plan_launch(h, S, st, &grid);
         if (rc != TTVB_OK) return rc;
         rc = dispatch_launch(h, S, grid, st);
         if (rc != TTVB_OK) return rc;
-        if (chi2_out) CU(cudaMemcpyAsync(chi2_out + b0, d + off_chi2, (size_t)nb * 8, cudaMemcpyDeviceToHost, st));
-        if (logl_out) CU(cudaMemcpyAsync(logl_out + b0, d + off_logl, (size_t)nb * 8, cudaMemcpyDeviceToHost, st));
-        if (chi2_planet_out) CU(cudaMemcpyAsync(chi2_planet_out + b0 * N, d + off_pl, (size_t)nb * N * 8, cudaMemcpyDeviceToHost, st));
-        if (status_out) CU(cudaMemcpyAsync(status_out + b0, d + off_st, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaEventRecord(h->ev_krn[bf], st));
+        if (k + 1 < nchunks) { rc = upload(k + 1); if (rc != TTVB_OK) return rc; }
+        cudaStream_t so = h->s_out;
+        CU(cudaStreamWaitEvent(so, h->ev_krn[bf], 0));
+        if (chi2_out) CU(cudaMemcpyAsync(chi2_out + b0, d + off_chi2, (size_t)nb * 8, cudaMemcpyDeviceToHost, so));
+        if (logl_out) CU(cudaMemcpyAsync(logl_out + b0, d + off_logl, (size_t)nb * 8, cudaMemcpyDeviceToHost, so));
+        if (chi2_planet_out) CU(cudaMemcpyAsync(chi2_planet_out + b0 * N, d + off_pl, (size_t)nb * N * 8, cudaMemcpyDeviceToHost, so));
+        if (status_out) CU(cudaMemcpyAsync(status_out + b0, d + off_st, (size_t)nb * 4, cudaMemcpyDeviceToHost, so));
         if (table) {
-            CU(cudaMemcpyAsync(n_events + b0, d + off_ne, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
-            CU(cudaMemcpyAsync(ev_planet + b0 * cap, d + off_ep, (size_t)nb * cap * 4, cudaMemcpyDeviceToHost, st));
-            CU(cudaMemcpyAsync(ev_epoch + b0 * cap, d + off_epo, (size_t)nb * cap * 4, cudaMemcpyDeviceToHost, st));
-            CU(cudaMemcpyAsync(ev_time + b0 * cap, d + off_et, (size_t)nb * cap * 8, cudaMemcpyDeviceToHost, st));
-            CU(cudaMemcpyAsync(ev_rsky + b0 * cap, d + off_er, (size_t)nb * cap * 8, cudaMemcpyDeviceToHost, st));
-            CU(cudaMemcpyAsync(ev_vsky + b0 * cap, d + off_ev, (size_t)nb * cap * 8, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(n_events + b0, d + off_ne, (size_t)nb * 4, cudaMemcpyDeviceToHost, so));
+            CU(cudaMemcpyAsync(ev_planet + b0 * cap, d + off_ep, (size_t)nb * cap * 4, cudaMemcpyDeviceToHost, so));
+            CU(cudaMemcpyAsync(ev_epoch + b0 * cap, d + off_epo, (size_t)nb * cap * 4, cudaMemcpyDeviceToHost, so));
+            CU(cudaMemcpyAsync(ev_time + b0 * cap, d + off_et, (size_t)nb * cap * 8, cudaMemcpyDeviceToHost, so));
+            CU(cudaMemcpyAsync(ev_rsky + b0 * cap, d + off_er, (size_t)nb * cap * 8, cudaMemcpyDeviceToHost, so));
+            CU(cudaMemcpyAsync(ev_vsky + b0 * cap, d + off_ev, (size_t)nb * cap * 8, cudaMemcpyDeviceToHost, so));
         }
+        CU(cudaEventRecord(h->ev_out[bf], so));
     }
+    // the caller's stream ends after the last download; ev1 closes the timed region there
+    for (int bf = 0; bf < nbuf; bf++) CU(cudaStreamWaitEvent(st, h->ev_out[bf], 0));
     CU(cudaEventRecord(h->ev1, st));
     CU(cudaEventRecord(h->ev_done, st));
     h->timed = true;

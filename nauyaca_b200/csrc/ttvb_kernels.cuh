@@ -243,9 +243,7 @@ __device__ __noinline__ void process_batch(const DevSys& S, int count, WarpQ Q, 
             xa[e][k] = first ? xs[e][0][k] : xs[e][1][k];
             va[e][k] = first ? vsn[e][0][k] : vsn[e][1][k];
         }
-        const double den = ga - gb;
-        tau_b[e] = (-gb / den) * S.dt;
-        tau_a[e] = (-ga / den) * S.dt;
+        first_guess(mu[e], S.dt, xb[e], vb[e], gb, xa[e], va[e], ga, tau_b[e], tau_a[e]);
     }
     double rb[2], vbk[2], ra[2], vak[2];
     bool okb[2], oka[2];

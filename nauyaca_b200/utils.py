@@ -111,15 +111,15 @@ def run_TTVFast(flat_params, mstar, init_time=0., final_time=None, dt=None):
 
 
 def _ephemeris(PSystem, SP):
-    """utils.py:84-123: per planet {epoch: time} of the events with rsky <= rstarAU."""
+    """utils.py:84-123: per planet {epoch: time} of the events with rsky <= rstarAU (one pass over the
+    event table; a malformed table prints the reference's warning and yields what was built)."""
     ephemeris = {}
     try:
-        for planet_id, planet_number in PSystem.planets_IDs.items():
-            planet_mask = SP[0] == planet_number
-            transit_mask = SP[3][planet_mask] <= PSystem.rstarAU
-            transit_number = SP[1][planet_mask][transit_mask].astype(int)
-            transit_time = SP[2][planet_mask][transit_mask]
-            ephemeris[planet_id] = dict(zip(transit_number, transit_time))
+        planet, epoch, time, rsky = (np.asarray(SP[k]) for k in range(4))
+        transits = rsky <= PSystem.rstarAU
+        for planet_id, number in PSystem.planets_IDs.items():
+            sel = transits & (planet == number)
+            ephemeris[planet_id] = {int(e): t for e, t in zip(epoch[sel], time[sel])}
     except Exception:
         print('Warning: Invalid proposal')
     return ephemeris
@@ -150,32 +150,30 @@ def _chi2(observed, sigma, simulated, individual=False):
 
 
 def intervals(frontiers, flat_params):
-    """utils.py:1193-1219: list of booleans, returned as soon as a False is produced."""
+    """utils.py:1193-1219: one boolean per parameter, cut short after the first False (callers only
+    ask whether False is in the list)."""
     TF = []
-    for i in range(len(flat_params)):
-        if frontiers[i][0] <= flat_params[i] <= frontiers[i][1]:
-            TF.append(True)
-        else:
-            TF.append(False)
-            return TF
+    for (lo, hi), value in zip(frontiers, flat_params):
+        TF.append(bool(lo <= value <= hi))
+        if not TF[-1]:
+            break
+    if len(frontiers) < len(flat_params) and (not TF or TF[-1]):
+        frontiers[len(frontiers)]           # the reference indexes past the bounds here: same IndexError
     return TF
 
 
 def _insert_constants(PSystem, x):
-    """utils.py:440-447."""
-    x = list(x)
-    for k, v in PSystem.constant_params.items():
-        x.insert(k, v)
-    return x
+    """utils.py:440-447: the constants go back to their flat indices, in ascending order."""
+    out = list(x)
+    for index in sorted(PSystem.constant_params):
+        out.insert(index, PSystem.constant_params[index])
+    return out
 
 
 def _remove_constants(PSystem, x):
-    """utils.py:450-460."""
-    indexes_remove = list(PSystem.constant_params.keys())
-    x = list(x)
-    for index in sorted(indexes_remove, reverse=True):
-        del x[index]
-    return np.array(x)
+    """utils.py:450-460: drop the slots of the constant parameters."""
+    skip = set(PSystem.constant_params.keys())
+    return np.array([v for k, v in enumerate(x) if k not in skip])
 
 
 def cube_to_physical(PSystem, x):

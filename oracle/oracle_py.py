@@ -11,14 +11,16 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "libttv_oracle.so")
+_LIB_NATIVE = os.path.join(_HERE, "libttv_oracle_native.so")     # timing build (bench.py CPU legs)
 
 ST_OUT_OF_BOUNDS, ST_KEPLER_FAIL, ST_BAD_TRANSIT, ST_EVENT_OVERFLOW, ST_INVALID_INPUT = 1, 2, 4, 8, 16
 
 
 def build(force=False):
     src = os.path.join(_HERE, "ttv_oracle.c")
-    if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < os.path.getmtime(src):
-        subprocess.check_call(["make", "-C", _HERE, "-B", "libttv_oracle.so"])
+    for so in (_LIB, _LIB_NATIVE):
+        if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+            subprocess.check_call(["make", "-C", _HERE, "-B", os.path.basename(so)])
     return _LIB
 
 
@@ -33,10 +35,19 @@ class _Sys(C.Structure):
 
 
 _lib = None
+_lib_native = None
 
 
-def lib():
-    global _lib
+def lib(native=False):
+    """The oracle library. native=True: the timing build (host divide/sqrt instead of the
+    emulated GPU seeds; last-bit differences) that bench.py's CPU legs time - never the checker."""
+    global _lib, _lib_native
+    if native:
+        if _lib_native is None:
+            if not os.path.exists(_LIB_NATIVE):
+                build()
+            _lib_native = C.CDLL(_LIB_NATIVE)
+        return _lib_native
     if _lib is None:
         if not os.path.exists(_LIB):
             build()
@@ -81,14 +92,14 @@ def nsteps(t0, total, dt):
     return int(lib().ttvo_nsteps(float(t0), float(total), float(dt)))
 
 
-def ephemeris(flat, mstar, t0, dt, total, cap=5000):
+def ephemeris(flat, mstar, t0, dt, total, cap=5000, native=False):
     """Engine seam S1: returns (status, planet[int], epoch[int], time, rsky, vsky)."""
     flat = np.ascontiguousarray(flat, dtype=np.float64)
     npla = flat.size // 7
     n = C.c_int(0)
     pl = np.zeros(cap, np.int32); ep = np.zeros(cap, np.int32)
     tm = np.zeros(cap); rs = np.zeros(cap); vs = np.zeros(cap)
-    st = lib().ttvo_ephemeris(_p(flat), C.c_int(npla), C.c_double(mstar), C.c_double(t0),
+    st = lib(native).ttvo_ephemeris(_p(flat), C.c_int(npla), C.c_double(mstar), C.c_double(t0),
                               C.c_double(dt), C.c_double(total), C.c_int(cap), C.byref(n),
                               _p(pl), _p(ep), _p(tm), _p(rs), _p(vs))
     k = n.value
@@ -98,10 +109,12 @@ def ephemeris(flat, mstar, t0, dt, total, cap=5000):
 class OracleSystem:
     """Frozen per-system constants (what planetarysystem.py:184-350 derives)."""
 
-    def __init__(self, spec):
+    def __init__(self, spec, native=False):
         """spec: dict with the keys of tests/golden/systems.json entries (or the
-        equivalent built from a PlanetarySystem by nauyaca_b200.system_spec)."""
+        equivalent built from a PlanetarySystem by nauyaca_b200.system_spec).
+        native=True: loglike() runs the timing build (see lib())."""
         self.spec = spec
+        self.native = bool(native)
         self.npla, self.ndim = int(spec["npla"]), int(spec["ndim"])
         self.bi = np.array(spec["bi"], np.float64); self.bf = np.array(spec["bf"], np.float64)
         self.hyper_lo = np.array([h[0] for h in spec["hypercube"]], np.float64)
@@ -141,8 +154,19 @@ class OracleSystem:
         B = X.shape[0]
         chi2 = np.zeros(B); logl = np.zeros(B); st = np.zeros(B, np.int32)
         s = self._struct(mode)
-        lib().ttvo_loglike_batch(C.byref(s), _p(X), C.c_long(B), C.c_int(mode), _p(chi2), _p(logl), _p(st))
+        lib(self.native).ttvo_loglike_batch(C.byref(s), _p(X), C.c_long(B), C.c_int(mode), _p(chi2), _p(logl), _p(st))
         return chi2, logl, st
+
+    def loglike_threads(self, X, mode=0, threads=None):
+        """loglike() with the rows spread over host threads (the C call releases the GIL): for
+        samples of long integrations (BASELINE config 4: about 10 ms per system)."""
+        from concurrent.futures import ThreadPoolExecutor
+        X = np.ascontiguousarray(np.atleast_2d(X), dtype=np.float64)
+        threads = threads or min(32, os.cpu_count() or 1)
+        parts = [p for p in np.array_split(np.arange(X.shape[0]), threads * 4) if p.size]
+        with ThreadPoolExecutor(threads) as ex:
+            res = list(ex.map(lambda idx: self.loglike(X[idx], mode), parts))
+        return tuple(np.concatenate([r[k] for r in res]) for k in range(3))
 
     def cube_to_physical(self, x):
         x = np.ascontiguousarray(x, np.float64)

@@ -17,11 +17,21 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF = "/root/reference"
 
 
+def reference_dir():
+    """The checkout (development container) or the copy __graft_entry__.build() left in
+    baseline/_ref (travels to the GPU box); None if neither exists."""
+    for cand in (REF, os.path.join(os.path.dirname(HERE), "baseline", "_ref")):
+        if os.path.isfile(os.path.join(cand, "nauyaca", "__init__.py")):
+            return cand
+    return None
+
+
 def import_reference():
-    """import nauyaca from the read-only checkout with the absent third-party modules stubbed
-    and `ttvfast` pointing at the shim. Returns (nauyaca, nauyaca.utils)."""
-    if not os.path.isdir(REF):
-        raise RuntimeError("/root/reference is not available on this machine")
+    """import nauyaca (unmodified) with the absent third-party modules stubbed and `ttvfast`
+    pointing at the oracle-backed shim. Returns (nauyaca, nauyaca.utils)."""
+    REF = reference_dir()
+    if REF is None:
+        raise RuntimeError("the reference package is not available on this machine")
     sys.path.insert(0, os.path.join(HERE, "ttvfast_shim"))
     for n in ["h5py", "ptemcee", "seaborn", "corner", "matplotlib", "matplotlib.pyplot", "matplotlib.ticker",
               "matplotlib.gridspec", "mpl_toolkits", "mpl_toolkits.axes_grid1", "sklearn", "sklearn.linear_model"]:
@@ -39,24 +49,21 @@ def import_reference():
     return nauyaca, utils
 
 
+def inputs_dir():
+    ref = reference_dir()
+    for cand in (os.path.join(ref, "inputs"), ref):
+        if os.path.isdir(os.path.join(cand, "Documentation", "inputs")):
+            return cand
+    raise RuntimeError("the reference's observation tables were not found")
+
+
 def build_systems(nau):
-    d = os.path.join(REF, "Documentation", "inputs")
-    Pb = nau.SetPlanet("Planet-b"); Pb.load_ttvs(os.path.join(d, "planetb_ttvs.dat"))
-    Pb.mass = [1, 50.]; Pb.period = [5.35, 5.36]; Pb.ecc = [0., 0.2]; Pb.inclination = [90, 90]; Pb.ascending_node = [88.36, 88.36]
-    Pc = nau.SetPlanet("Planet-c"); Pc.load_ttvs(os.path.join(d, "planetc_ttvs.dat"))
-    Pc.mass = [1, 50]; Pc.period = [11.83, 11.84]; Pc.ecc = [0, .2]; Pc.inclination = [90, 90]; Pc.ascending_node = [70, 110.]
-    doc2 = nau.PlanetarySystem("SystemX", mstar=0.9132, rstar=0.8632); doc2.add_planets([Pb, Pc])
-    doc2.simulation(t0=0.0, ftime=221, dt=0.18)
-    e = os.path.join(REF, "Examples", "inputs")
-    P1 = nau.SetPlanet('Planet-b'); P1.mass = [0.001, 10]; P1.period = [10.47, 10.48]; P1.ecc = [0.0, 0.1]
-    P1.inclination = [90, 90]; P1.ascending_node = [60, 120]; P1.load_ttvs(os.path.join(e, "3pl_planet1_ttvs.dat"))
-    P2 = nau.SetPlanet('Planet-c'); P2.mass = [0.001, 10]; P2.period = [14.10, 14.11]; P2.ecc = [0.0, 0.1]
-    P2.inclination = [85, 95]; P2.ascending_node = [60, 120]; P2.load_ttvs(os.path.join(e, "3pl_planet2_ttvs.dat"))
-    P3 = nau.SetPlanet('Planet-d'); P3.mass = [0.001, 10]; P3.period = [23.57, 23.58]; P3.ecc = [0.0, 0.1]
-    P3.inclination = [90.3, 90.3]; P3.ascending_node = [88.5, 88.5]; P3.load_ttvs(os.path.join(e, "3pl_planet3_ttvs.dat"))
-    sys3 = nau.PlanetarySystem("MySystem", mstar=0.522, rstar=0.4422); sys3.add_planets([P1, P2, P3])
-    sys3.simulation(t0=0, ftime=500)
-    return {"doc2": doc2, "sys3": sys3}
+    """doc2 / sys3 / sys3f built with the reference's own classes (oracle/ref_systems.py)."""
+    root = os.path.dirname(HERE)
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    from oracle import ref_systems
+    return ref_systems.build(nau, inputs_dir())
 
 
 _PS = None
@@ -78,6 +85,7 @@ def _work(x):
 def main():
     import multiprocessing as mp
     import numpy as np
+    os.environ["TTVO_NATIVE"] = "1"     # timing: host divide/sqrt, not the emulated GPU seeds
     cores = os.cpu_count() or 1
     for name, n in (("doc2", 4000), ("sys3", 4000)):
         _init(name)

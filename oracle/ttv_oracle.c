@@ -233,6 +233,14 @@ static double seed_rsq(double a)
 }
 
 /* 1/b: cubic refinement of the seed (relative error of the seed below 2^-19) */
+#ifdef TTVO_NATIVE_RCP
+/* Timing build (libttv_oracle_native.so, bench.py's CPU legs only): the host's own divide and
+ * square root instead of the emulated GPU seeds, whose 12 MB of table look-ups cost a CPU four
+ * times the arithmetic. Same algorithm, last-bit differences; never used as the checker. */
+static double rcp_fast(double b) { return 1.0 / b; }
+static double rsqrt_fast(double a) { return 1.0 / sqrt(a); }
+void ttvo_unused_seed_refs(void) { (void)seed_rcp; (void)seed_rsq; }
+#else
 static double rcp_fast(double b)
 {
     double y0 = seed_rcp(b);
@@ -251,6 +259,7 @@ static double rsqrt_fast(double a)
     double h = y0 * e;
     return fma(p, h, y0);
 }
+#endif
 
 /* ------------------------------------------------------------------ */
 /* Stumpff functions c2,c3 by series with argument quartering (A.9)    */
@@ -551,7 +560,23 @@ static int prologue(const double *flat, int n, double mstar, consts_t *C, state_
 /* ------------------------------------------------------------------ */
 static double sky_g(const double *x, const double *v) { return fma(x[1], v[1], x[0] * v[0]); }
 
-/* Newton on g(tau)=x.vx+y.vy=0 along the two-body orbit through (x0,v0); returns status */
+/* dg/dt = vx^2 + vy^2 - mu (x^2+y^2)/r^3 along a two-body orbit; also x^2+y^2 and vx^2+vy^2 */
+static double sky_gp(double mu, const double *x, const double *v, double *rs2_out, double *vs2_out)
+{
+    double rs2 = fma(x[1], x[1], x[0] * x[0]);
+    double vs2 = fma(v[1], v[1], v[0] * v[0]);
+    double r2 = fma(x[2], x[2], rs2);
+    double ir = rsqrt_fast(r2);
+    *rs2_out = rs2; *vs2_out = vs2;
+    return fma(-mu * rs2, ir * ir * ir, vs2);
+}
+
+long ttvo_locate_evals;      /* diagnostics: Kepler drifts spent in locate_side */
+
+/* Newton on g(tau)=x.vx+y.vy=0 along the two-body orbit through (x0,v0); returns status.
+ * Stops when the step taken is below 1e-7 d: Newton converges quadratically here
+ * (|g''/2g'| < 1/d), so the iterate it has just moved to is within 1e-14 d of the root. */
+#define TTVO_TR_TOL 1e-7
 static int locate_side(double mu, const double *x0, const double *v0, double *tau,
                        double *rsky, double *vsky)
 {
@@ -559,15 +584,13 @@ static int locate_side(double mu, const double *x0, const double *v0, double *ta
     for (int it = 0; it < TTVO_TR_MAXIT; it++) {
         double x[3] = {x0[0], x0[1], x0[2]}, v[3] = {v0[0], v0[1], v0[2]};
         if (kepler_drift(mu, t, x, v)) return ST_BAD_TRANSIT;
+        ttvo_locate_evals++;
         double g = sky_g(x, v);
-        double rs2 = fma(x[1], x[1], x[0] * x[0]);
-        double vs2 = fma(v[1], v[1], v[0] * v[0]);
-        double r2 = fma(x[2], x[2], rs2);
-        double ir = rsqrt_fast(r2);
-        double gp = fma(-mu * rs2, ir * ir * ir, vs2);
+        double rs2, vs2;
+        double gp = sky_gp(mu, x, v, &rs2, &vs2);
         double d = -g * rcp_fast(gp);
         t = t + d;
-        if (fabs(d) <= 1e-13) {
+        if (fabs(d) <= TTVO_TR_TOL) {
             *tau = t; *rsky = sqrt(rs2); *vsky = sqrt(vs2);
             return 0;
         }
@@ -606,9 +629,19 @@ static int locate_event(const consts_t *C, const state_t *p3, const double *T3, 
     double gb, ga, Tb, Ta;
     if (other == 0) { xb = xo; vb = vo; gb = go; Tb = T3[0]; xa = xm; va = vm; ga = gm; Ta = T3[1]; }
     else            { xb = xm; vb = vm; gb = gm; Tb = T3[1]; xa = xo; va = vo; ga = go; Ta = T3[2]; }
+    /* first guess of the root: INVERSE cubic Hermite interpolation of t(g) between the two nodes
+     * (values 0 and dt, slopes 1/g' at the nodes) evaluated at g = 0; s is the secant fraction.
+     * Outside [0, dt] (or NaN) it falls back to the secant point. */
     double den = ga - gb;
-    double tau_b = (-gb / den) * dt;
-    double tau_a = (-ga / den) * dt;
+    double s = -gb * rcp_fast(den);
+    double u1, u2;
+    double qb = den * rcp_fast(sky_gp(C->mu[i], xb, vb, &u1, &u2));
+    double qa = den * rcp_fast(sky_gp(C->mu[i], xa, va, &u1, &u2));
+    double oms = 1.0 - s, s2 = s * s;
+    double h10 = s * oms * oms, h01 = s2 * fma(-2.0, s, 3.0), h11 = -s2 * oms;
+    double tau_b = fma(h10, qb, fma(h01, dt, h11 * qa));
+    if (!(tau_b >= 0.0 && tau_b <= dt)) tau_b = s * dt;
+    double tau_a = tau_b - dt;
     double rb, vbk, ra, vak;
     int st = locate_side(C->mu[i], xb, vb, &tau_b, &rb, &vbk);
     st |= locate_side(C->mu[i], xa, va, &tau_a, &ra, &vak);

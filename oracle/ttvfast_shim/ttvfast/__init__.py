@@ -25,7 +25,10 @@ def ttvfast(planets, stellar_mass, time, dt, total, rv_times=None, input_flag=1)
         # utils.py:62 multiplied by Mearth_to_Msun; undo with the same constant (exact for the
         # golden vectors is not required here: the oracle multiplies again, see tests)
         flat += [p.mass / _MEARTH, p.period, p.eccentricity, p.inclination, p.argument, p.mean_anomaly, p.longnode]
-    st, pl, ep, tm, rs, vs = oracle_py.ephemeris(flat, stellar_mass, time, dt, total, cap=N_EVENTS)
+    # TTVO_NATIVE=1 (bench.py's reference-plumbing timing leg): the oracle build with the host's own
+    # divide / sqrt instead of the emulated GPU seeds
+    st, pl, ep, tm, rs, vs = oracle_py.ephemeris(flat, stellar_mass, time, dt, total, cap=N_EVENTS,
+                                                 native=os.environ.get("TTVO_NATIVE") == "1")
     pad = [-2] * (N_EVENTS - len(tm))
     pos = [pl.tolist() + pad, ep.tolist() + pad, tm.tolist() + pad, rs.tolist() + pad, vs.tolist() + pad]
     return {"positions": pos, "rv": None}

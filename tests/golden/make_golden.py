@@ -220,5 +220,33 @@ def main():
               "nobs", [len(o["epochs"]) for o in v["observed"].values()])
 
 
+def g5():
+    """Regenerate the regression values of g5_long_baseline.json: the
+    `trues` 3-planet solution (Examples/inputs/trues:13-23) against the full 1359-d tables, with
+    the oracle. Needs only systems.json; run after a deliberate change of the canonical arithmetic
+    and check that the two-decimal values of the survey's probe (78.56 / 44.08 / 30.38) still hold."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from oracle import oracle_py as o
+    path = os.path.join(HERE, "g5_long_baseline.json")
+    with open(path) as fh:
+        g = json.load(fh)
+    with open(os.path.join(HERE, "systems.json")) as fh:
+        spec = dict(json.load(fh)[g["system"]])
+    spec["mstar"], spec["rstarAU"] = g["mstar"], g["rstar"] * g["Rsun_to_AU"]
+    osys = o.OracleSystem(spec)
+    for dt, key in ((spec["dt"], "chi2_regression"), (0.1, "chi2_regression_dt0.1")):
+        st, pl, ep, tm, rs, vs = o.ephemeris(g["flat_params"], spec["mstar"], spec["t0"], dt, spec["ftime"])
+        tot, per = osys.chi2_from_events(pl, ep, tm, rs)
+        assert st == 0 and [int((pl == i).sum()) for i in range(3)] == g["n_events"]
+        assert all(abs(float(p) - q) <= 0.0051 for p, q in zip(per, g["chi2_survey_2dec"]))
+        g[key] = [float(p) for p in per]
+    with open(path, "w") as fh:
+        json.dump(g, fh, indent=1)
+    print("wrote", path)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "g5":
+        g5()
+    else:
+        main()

@@ -194,11 +194,20 @@ def test_c4_full_size_properties(oracle):
     idx = rng.permutation(100_000)[:5000]
     chi2s, _, _ = eng.loglike(X[idx], mode=0)
     assert np.array_equal(chi2s, chi2[idx])
-    # a sample against the oracle, bit for bit
+    # a sample of 512 walkers against the oracle, bit for bit (host threads: ~10 ms per system)
     osys = oracle.OracleSystem(spec)
-    pick = idx[:12]
-    oc, ol, ost = osys.loglike(X[pick], mode=0)
-    assert np.array_equal(oc, chi2[pick]) and np.array_equal(ol, logl[pick])
+    pick = idx[:512]
+    oc, ol, ost = osys.loglike_threads(X[pick], mode=0)
+    assert np.array_equal(oc, chi2[pick]) and np.array_equal(ol, logl[pick]) and np.all(ost == 0)
+    # ... and the whole event table (planet, epoch, time, rsky, vsky) of 32 of them at 15001 steps
+    flat = np.stack([osys.cube_to_physical(x) for x in X[pick[:32]]])
+    n, pl, ep, tm, rs, vs, st2 = eng.ephemeris(flat, mode=2)
+    for b in range(32):
+        o = oracle.ephemeris(flat[b], spec["mstar"], spec["t0"], spec["dt"], spec["ftime"])
+        k = int(n[b])
+        assert o[0] == st2[b] == 0 and k == len(o[3]) and k > 300
+        assert np.array_equal(pl[b, :k], o[1]) and np.array_equal(ep[b, :k], o[2])
+        assert np.array_equal(tm[b, :k], o[3]) and np.array_equal(rs[b, :k], o[4]) and np.array_equal(vs[b, :k], o[5])
     eng.close()
 
 
@@ -225,4 +234,30 @@ def test_c5_full_sweep_streams_in_chunks(oracle, systems):
     pick = idx[::200]
     oc, ol, ost = osys.loglike(X[pick], mode=0)
     assert np.array_equal(oc, chi2[pick]) and np.array_equal(ost, st[pick])
+    eng.close()
+
+
+@pytest.mark.parametrize("dt,key", [(0.34874, "chi2_regression"), (0.1, "chi2_regression_dt0.1")])
+def test_g5_long_baseline_on_gpu(oracle, systems, dt, key):
+    """SURVEY section 4, G5 on the GPU: the 1359-d baseline (3897 and 13591 steps), 285 events, none masked,
+    chi2 78.56 / 44.08 / 30.38, event table and chi2 equal to the oracle's bit for bit."""
+    import nauyaca_b200 as nb
+    from test_oracle_golden import g5_spec
+    g5, spec = g5_spec(systems)
+    spec["dt"] = dt
+    eng = nb.BatchEngine(spec); osys = oracle.OracleSystem(spec)
+    flat = np.array([g5["flat_params"]])
+    chi2, logl, st, per = eng.loglike(flat, mode=2, per_planet=True)
+    assert st[0] == 0
+    for i in range(3):
+        assert abs(per[0, i] - g5["chi2_survey_2dec"][i]) <= 0.0051
+        assert abs(per[0, i] - g5[key][i]) <= 1e-6 * g5[key][i]
+    oc, ol, ost = osys.loglike(flat, mode=2)
+    assert chi2[0] == oc[0] and logl[0] == ol[0]
+    n, pl, ep, tm, rs, vs, st2 = eng.ephemeris(flat, mode=2)
+    o = oracle.ephemeris(flat[0], spec["mstar"], spec["t0"], dt, spec["ftime"])
+    k = int(n[0])
+    assert k == 285 and [int((pl[0, :k] == i).sum()) for i in range(3)] == g5["n_events"]
+    assert np.array_equal(tm[0, :k], o[3]) and np.array_equal(ep[0, :k], o[2]) and np.array_equal(rs[0, :k], o[4])
+    assert np.all(rs[0, :k] <= spec["rstarAU"])
     eng.close()
