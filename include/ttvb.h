@@ -49,6 +49,8 @@ extern "C" {
 #define TTVB_ST_BAD_TRANSIT 4     /* a transit refinement failed; its time is -1 (TTVFast BAD_TRANSIT) */
 #define TTVB_ST_EVENT_OVERFLOW 8  /* more events than `cap` in ttvb_ephemeris */
 #define TTVB_ST_INVALID_INPUT 16  /* non-finite / non-elliptic elements */
+#define TTVB_ST_INPUT_TIMEOUT 32  /* host-pointer call: the rows of this system never arrived on the device (a
+                                   * failed upload; the call itself returns an error). Never set otherwise. */
 
 /* interpretation of the rows of `x` */
 #define TTVB_MODE_CUBE 0          /* x[B][ndim] in the unit hypercube: intervals(PS.hypercube) then
@@ -206,6 +208,15 @@ int ttvb_selftest_perm(uint32_t n, uint32_t k0, uint32_t k1, uint32_t *perm_out)
  * hi, lookup hi) of one offending word each, if any. */
 int ttvb_selftest_seed_scan(int device, const uint32_t *rcp_tab, const uint32_t *rsq_tab, uint64_t mismatches[2],
                             uint32_t first_bad[6]);
+
+/* Self-checks build (nvcc -DTTVB_CHECKS; compute-sanitizer is not available on the GPU pool): the
+ * kernels verify the indices of their queue / ring / result-area / observed-table / event-table
+ * accesses and bound their inter-CTA waits, counting violations by kind:
+ * counts[0] queue slot, [1] batch header, [2] fold, [3] observed-table index, [4] event-table index,
+ * [5] hand-over wait timed out, [6] work-unit decoding. Returns TTVB_E_UNSUPPORTED (counts = -1) from
+ * the product build, which compiles the checks away. tests/test_gpu_checks.py runs the cases a
+ * sanitizer run would have covered against such a build. */
+int ttvb_check_failures(int device, int32_t counts[8]);
 
 #ifdef __cplusplus
 }

@@ -31,7 +31,7 @@ EXPORTS = ["ttvb_last_error", "ttvb_version", "ttvb_device_count", "ttvb_create"
            "ttvb_set_cube_bounds", "ttvb_nsteps", "ttvb_loglike", "ttvb_ephemeris", "ttvb_cube_to_physical",
            "ttvb_last_kernel_ms", "ttvb_launch_count", "ttvb_fp64_peak",
            "ttvb_pt_create", "ttvb_pt_destroy", "ttvb_pt_set_walkers", "ttvb_pt_run", "ttvb_pt_get", "ttvb_pt_half_begin", "ttvb_pt_half_end", "ttvb_pt_proposal_logl",
-           "ttvb_selftest_philox", "ttvb_selftest_perm", "ttvb_selftest_seed_scan"]
+           "ttvb_selftest_philox", "ttvb_selftest_perm", "ttvb_selftest_seed_scan", "ttvb_check_failures"]
 
 
 class TTVBError(RuntimeError):
@@ -55,6 +55,23 @@ def needs_build():
         return True
     t = os.path.getmtime(LIB_PATH)
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in DEPS)
+
+
+CHECKS_LIB_PATH = os.path.join(_HERE, "libttvb_checks.so")
+
+
+def build_checks(force=False):
+    """The self-checking build (nvcc -DTTVB_CHECKS, 2- and 3-planet kernels only): see
+    ttvb_check_failures in include/ttvb.h. Used by tests/test_gpu_checks.py in a subprocess
+    (TTVB_LIB=...); never loaded by the product path."""
+    if not force and os.path.exists(CHECKS_LIB_PATH) and \
+            all(os.path.getmtime(d) <= os.path.getmtime(CHECKS_LIB_PATH) for d in DEPS if os.path.exists(d)):
+        return CHECKS_LIB_PATH
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    tmp = CHECKS_LIB_PATH + f".tmp{os.getpid()}"
+    subprocess.check_call([nvcc] + NVCC_FLAGS + ["-DTTVB_CHECKS", "-DTTVB_DEV_ONLY_23", "-o", tmp, SRC])
+    os.replace(tmp, CHECKS_LIB_PATH)
+    return CHECKS_LIB_PATH
 
 
 def build(force=False, verbose=False):
@@ -124,6 +141,7 @@ def lib():
     L.ttvb_pt_proposal_logl.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.ttvb_fp64_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_float)]
     L.ttvb_selftest_seed_scan.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ttvb_check_failures.argtypes = [C.c_int, C.c_void_p]
     _lib = L
     return L
 

@@ -66,8 +66,11 @@ struct ttvb_handle {
     cudaEvent_t ev_done = nullptr;   // end of the last launch that used the handle's scratch state
     // host-pointer calls: copy-in / copy-out streams and the events of the two staging buffers
     cudaStream_t s_in = nullptr, s_out = nullptr;
+    int* h_ready = nullptr;          // pinned: row counts the copy-in stream writes to the device counter
+    size_t h_ready_cap = 0;          // (one slot per upload piece of a call: a slot is read when its copy EXECUTES)
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_krn[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     bool timed = false;
+    bool in_capture = false;     // the call is being captured into a CUDA graph: no events, no waits on outside work
     long long launches = 0;
 };
 
@@ -77,7 +80,16 @@ template <int N>
 int configure(ttvb_handle* h) {
     // worst-case dynamic shared memory over the three modes
     size_t smem = ttvb::smem_bytes(N, h->nobs, 7 * N);
-    CU(cudaFuncSetAttribute(ttvb::ttvb_main_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // The attribute belongs to the FUNCTION, not to the handle: a second handle with a smaller
+    // observed table must not lower it under the first one's launches. Opt in to the device's
+    // limit once; every launch then asks for what it needs.
+    int optin = 0;
+    CU(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+    cudaFuncAttributes fa;
+    CU(cudaFuncGetAttributes(&fa, ttvb::ttvb_main_kernel<N>));
+    optin -= (int)fa.sharedSizeBytes;                 // the opt-in limit covers static + dynamic shared memory
+    if (smem > (size_t)optin) return fail(TTVB_E_UNSUPPORTED, "observed table too large for shared memory (%zu B needed, %d B available)", smem, optin);
+    CU(cudaFuncSetAttribute(ttvb::ttvb_main_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
     int nb = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ttvb::ttvb_main_kernel<N>, TTVB_TPB, smem));
     if (nb < 1) return fail(TTVB_E_CUDA, "kernel does not fit on an SM (smem %zu B)", smem);
@@ -369,6 +381,7 @@ int ttvb_destroy(ttvb_handle* h) {
         if (h->ev_krn[i]) cudaEventDestroy(h->ev_krn[i]);
         if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]);
     }
+    if (h->h_ready) cudaFreeHost(h->h_ready);
     if (h->s_in) cudaStreamDestroy(h->s_in);
     if (h->s_out) cudaStreamDestroy(h->s_out);
     delete h;
@@ -412,20 +425,21 @@ static int run_batch(ttvb_handle* h, const double* x, int64_t B, int mode, doubl
     set_mode(h, S, mode);
     const int rowlen = S.rowlen, N = h->npla;
     S.cap = cap;
-    h->timed = false;
+    if (!h->in_capture) h->timed = false;
     // The handle's scratch state (unit counter and segment flags, event queues, hand-over
     // context, staging) is shared by all its launches: a call on another stream first waits for
     // the previous launch of this handle, so two streams can never run on it at the same time.
-    CU(cudaStreamWaitEvent(st, h->ev_done, 0));
+    if (!h->in_capture) CU(cudaStreamWaitEvent(st, h->ev_done, 0));
 
     if (dev) {
-        S.B = B; S.x = x;
+        S.B = B; S.x = x; S.ready = nullptr;
         S.chi2_out = chi2_out; S.logl_out = logl_out; S.chi2_planet_out = chi2_planet_out; S.status_out = status_out;
         S.n_events = n_events; S.ev_planet = ev_planet; S.ev_epoch = ev_epoch;
         S.ev_time = ev_time; S.ev_rsky = ev_rsky; S.ev_vsky = ev_vsky;
         int grid = 0;
         int rc = plan_launch(h, S, st, &grid);
         if (rc != TTVB_OK) return rc;
+        if (h->in_capture) return dispatch_launch(h, S, grid, st);
         CU(cudaEventRecord(h->ev0, st));
         rc = dispatch_launch(h, S, grid, st);
         if (rc != TTVB_OK) return rc;
@@ -435,34 +449,23 @@ static int run_batch(ttvb_handle* h, const double* x, int64_t B, int mode, doubl
         return TTVB_OK;
     }
 
-    // host pointers: the batch is cut into chunks that flow through TWO staging buffers, so that
-    // the upload of chunk k+1 (copy-in stream) and the download of chunk k-1 (copy-out stream)
-    // run under the kernel of chunk k (caller's stream). The kernels themselves stay in order on
-    // `st` (they share the handle's scheduling state). Returns after the results are on the host.
-    // Chunk schedule: whole waves (one wave = as many systems as the resident CTAs hold, so a chunk
-    // leaves no partly filled round behind), the first chunk ONE wave so that only a small upload is
-    // exposed before the first kernel starts, then doubling up to ~2^20 systems.
+    // host pointers: STREAMED. The batch is cut into launches of up to ~2^20 systems that alternate
+    // between two staging buffers. The kernel of a launch starts at once and its tiles wait (on the
+    // device) for their rows: the copy-in stream uploads them in pieces of whole waves, 1 wave first
+    // and doubling (one wave = as many systems as the resident CTAs hold), bumping a row counter
+    // after each piece. So only the first small upload is exposed, there is no kernel boundary
+    // inside a launch, the uploads of launch k+1 run under the kernel of launch k, and the results
+    // of launch k are downloaded (copy-out stream) under launch k+1. The kernels themselves stay in
+    // order on `st` (they share the handle's scheduling state). Returns after the results are on
+    // the host.
     const long long wave = (long long)h->max_grid * h->tpb;
     long long cap_sys = std::max<long long>(wave, (CHUNK / wave) * wave);
     if (table) {
-        // an event table needs cap*28 bytes per system: bound the staging of one chunk to ~0.5 GiB
+        // an event table needs cap*28 bytes per system: bound the staging of one launch to ~0.5 GiB
         const size_t per_sys = (size_t)cap * 32 + (size_t)rowlen * 8 + 64;
         cap_sys = std::max<long long>(1, std::min<long long>(cap_sys, (long long)(((size_t)1 << 29) / per_sys)));
     }
-    std::vector<long long> starts, sizes;
-    {
-        long long b0 = 0, next = std::min<long long>(wave, cap_sys);
-        while (b0 < B) {
-            long long nb = std::min<long long>(next, B - b0);
-            const long long rem = B - b0 - nb;
-            if (!table && rem > 0 && rem < wave / 2) nb += rem;          // no tiny last chunk
-            starts.push_back(b0); sizes.push_back(nb);
-            b0 += nb;
-            next = std::min<long long>(cap_sys, next * 2);
-        }
-    }
-    long long chunk = 0;
-    for (long long v : sizes) chunk = std::max(chunk, v);
+    const long long chunk = std::min<long long>(B, cap_sys);
     size_t off_x = 0, bytes = align256((size_t)chunk * rowlen * 8);
     size_t off_chi2 = bytes; bytes += align256((size_t)chunk * 8);
     size_t off_logl = bytes; bytes += align256((size_t)chunk * 8);
@@ -477,29 +480,40 @@ static int run_batch(ttvb_handle* h, const double* x, int64_t B, int mode, doubl
         off_er = bytes;  bytes += align256((size_t)chunk * cap * 8);
         off_ev = bytes;  bytes += align256((size_t)chunk * cap * 8);
     }
-    const long long nchunks = (long long)sizes.size();
+    const size_t off_ready = bytes; bytes += 256;
+    const long long nchunks = (B + chunk - 1) / chunk;
     const int nbuf = nchunks > 1 ? 2 : 1;
     int rc = ensure_stage(h, bytes * nbuf);
     if (rc != TTVB_OK) return rc;
     rc = ensure_copy_streams(h);
     if (rc != TTVB_OK) return rc;
+    {
+        // one pinned slot per upload piece of this call (at most ~log2(chunk/wave)+2 pieces per launch)
+        size_t per_launch = 2;
+        for (long long w = wave; w < chunk; w *= 2) per_launch++;
+        const size_t need = (size_t)nchunks * per_launch;
+        if (need > h->h_ready_cap) {
+            if (h->h_ready) CU(cudaFreeHost(h->h_ready));
+            h->h_ready = nullptr; h->h_ready_cap = 0;
+            CU(cudaMallocHost(&h->h_ready, need * sizeof(int)));
+            h->h_ready_cap = need;
+        }
+    }
+    size_t slot = 0;
     CU(cudaEventRecord(h->ev0, st));
-    auto upload = [&](long long k) -> int {
-        const int bf = (int)(k % nbuf);
-        const long long b0 = starts[k], nb = sizes[k];
-        unsigned char* d = h->d_stage + (size_t)bf * bytes;
-        if (k >= nbuf) CU(cudaStreamWaitEvent(h->s_in, h->ev_out[bf], 0));      // buffer free again (chunk k-2 downloaded)
-        CU(cudaMemcpyAsync(d + off_x, x + b0 * rowlen, (size_t)nb * rowlen * 8, cudaMemcpyHostToDevice, h->s_in));
-        CU(cudaEventRecord(h->ev_in[bf], h->s_in));
-        return TTVB_OK;
-    };
-    rc = upload(0);
-    if (rc != TTVB_OK) return rc;
     for (long long k = 0; k < nchunks; k++) {
         const int bf = (int)(k % nbuf);
-        const long long b0 = starts[k], nb = sizes[k];
+        const long long b0 = k * chunk, nb = std::min<long long>(chunk, B - b0);
         unsigned char* d = h->d_stage + (size_t)bf * bytes;
+        int* d_ready = (int*)(d + off_ready);
+        // ---- copy-in stream: the buffer is free once launch k-2 has been downloaded; zero the row
+        //      counter, then upload the rows piece by piece
+        if (k >= nbuf) CU(cudaStreamWaitEvent(h->s_in, h->ev_out[bf], 0));
+        CU(cudaMemsetAsync(d_ready, 0, 4, h->s_in));
+        CU(cudaEventRecord(h->ev_in[bf], h->s_in));
+        // ---- caller's stream: the kernel (its tiles wait for their rows)
         S.B = nb; S.x = (const double*)(d + off_x);
+        S.ready = d_ready;
         S.chi2_out = chi2_out ? (double*)(d + off_chi2) : nullptr;
         S.logl_out = logl_out ? (double*)(d + off_logl) : nullptr;
         S.chi2_planet_out = chi2_planet_out ? (double*)(d + off_pl) : nullptr;
@@ -511,14 +525,31 @@ static int run_batch(ttvb_handle* h, const double* x, int64_t B, int mode, doubl
             S.n_events = nullptr; S.ev_planet = nullptr; S.ev_epoch = nullptr;
             S.ev_time = nullptr; S.ev_rsky = nullptr; S.ev_vsky = nullptr;
         }
-        CU(cudaStreamWaitEvent(st, h->ev_in[bf], 0));
+        CU(cudaStreamWaitEvent(st, h->ev_in[bf], 0));          // counter zeroed (and buffer free)
         int grid = 0;
         rc = plan_launch(h, S, st, &grid);
         if (rc != TTVB_OK) return rc;
         rc = dispatch_launch(h, S, grid, st);
         if (rc != TTVB_OK) return rc;
         CU(cudaEventRecord(h->ev_krn[bf], st));
-        if (k + 1 < nchunks) { rc = upload(k + 1); if (rc != TTVB_OK) return rc; }
+        // ---- uploads (after the launch call, so that a pageable source, whose copies block the host,
+        //      cannot delay the launch)
+        {
+            long long done = 0, piece = std::min<long long>(wave, nb);
+            while (done < nb) {
+                long long n = std::min<long long>(piece, nb - done);
+                if (nb - done - n < wave / 2) n = nb - done;               // no tiny last piece
+                CU(cudaMemcpyAsync(d + off_x + (size_t)done * rowlen * 8, x + (b0 + done) * rowlen, (size_t)n * rowlen * 8,
+                                   cudaMemcpyHostToDevice, h->s_in));
+                done += n;
+                if (slot >= h->h_ready_cap) return fail(TTVB_E_INVALID, "internal: upload piece count");
+                int* hv = h->h_ready + slot++;
+                *hv = (int)done;
+                CU(cudaMemcpyAsync(d_ready, hv, 4, cudaMemcpyHostToDevice, h->s_in));
+                piece *= 2;
+            }
+        }
+        // ---- copy-out stream: results of this launch
         cudaStream_t so = h->s_out;
         CU(cudaStreamWaitEvent(so, h->ev_krn[bf], 0));
         if (chi2_out) CU(cudaMemcpyAsync(chi2_out + b0, d + off_chi2, (size_t)nb * 8, cudaMemcpyDeviceToHost, so));
@@ -571,7 +602,7 @@ int ttvb_cube_to_physical(ttvb_handle* h, const double* x, int64_t B, double* fl
     set_mode(h, S, TTVB_MODE_CUBE);
     const int nf = 7 * h->npla;
     if (dev) {
-        S.B = B; S.x = x;
+        S.B = B; S.x = x; S.ready = nullptr;
         ttvb::ttvb_cube_to_physical_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(S, flat_out, inside_out);
         CU(cudaGetLastError());
         h->launches++;
@@ -625,6 +656,12 @@ struct ttvb_pt {
     long long time = 0;
     int hb = 1;
     double* d_block = nullptr;     // one allocation carved into the arrays of S
+    // one PT iteration captured as a CUDA graph (per value of `adapt`), replayed by ttvb_pt_run
+    cudaStream_t gs = nullptr;
+    cudaGraphExec_t gexec[2] = {nullptr, nullptr};
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    long long launches_per_iter = 0;
+    bool use_graph = true;
 };
 
 extern "C" {
@@ -644,7 +681,7 @@ int ttvb_pt_create(ttvb_handle* h, int32_t ntemps, int32_t nwalkers, const doubl
     const size_t nt = ntemps, nw = nwalkers, dim = h->ndim, half = nw / 2;
     const size_t n_p = nt * nw * dim, n_l = nt * nw, n_q = nt * half * dim, n_h = nt * half;
     const size_t pad = 64;         // room behind qlogl for the padded all-gather of sharded runs
-    const size_t total = n_p + n_l + nt + n_q + n_h + pad + n_h + 2 * n_l + 2 * nt + nt;
+    const size_t total = n_p + n_l + nt + n_q + n_h + pad + n_h + 2 * n_l + 2 * nt + nt + 1;
     if (cudaMalloc(&pt->d_block, total * 8) != cudaSuccess) { delete pt; return fail(TTVB_E_CUDA, "cudaMalloc(PT state) failed"); }
     cudaMemset(pt->d_block, 0, total * 8);
     double* c = pt->d_block;
@@ -653,7 +690,9 @@ int ttvb_pt_create(ttvb_handle* h, int32_t ntemps, int32_t nwalkers, const doubl
     S.p = c; c += n_p; S.logl = c; c += n_l; S.betas = c; c += nt; S.q = c; c += n_q; S.qlogl = c; c += n_h + pad;
     S.lnz = c; c += n_h; S.nprop = c; c += n_l; S.nprop_acc = c; c += n_l; S.nswap = c; c += nt; S.nswap_acc = c; c += nt;
     S.ratios = c; c += nt;
+    S.time_dev = reinterpret_cast<long long*>(c); c += 1;          // zeroed with the block
     S.seed0 = (uint32_t)seed; S.seed1 = (uint32_t)(seed >> 32);
+    if (const char* e = std::getenv("TTVB_PT_GRAPH")) pt->use_graph = std::atoi(e) != 0;
     int bits = 1;
     while ((1u << bits) < (unsigned)nwalkers) bits++;
     pt->hb = (bits + 1) / 2;
@@ -664,6 +703,10 @@ int ttvb_pt_create(ttvb_handle* h, int32_t ntemps, int32_t nwalkers, const doubl
 
 int ttvb_pt_destroy(ttvb_pt* pt) {
     if (!pt) return TTVB_OK;
+    for (int i = 0; i < 2; i++) if (pt->gexec[i]) cudaGraphExecDestroy(pt->gexec[i]);
+    if (pt->ev_a) cudaEventDestroy(pt->ev_a);
+    if (pt->ev_b) cudaEventDestroy(pt->ev_b);
+    if (pt->gs) cudaStreamDestroy(pt->gs);
     if (pt->d_block) cudaFree(pt->d_block);
     delete pt;
     return TTVB_OK;
@@ -681,33 +724,81 @@ int ttvb_pt_set_walkers(ttvb_pt* pt, const double* p0, void* stream) {
                      nullptr, nullptr, stream);
 }
 
+// One PT iteration on stream `st`: propose -> likelihood of the proposals -> accept, twice, then the
+// fused swap / bookkeeping / ladder kernel (which also advances the device-side iteration counter).
+static int pt_iteration(ttvb_pt* pt, int adapt, cudaStream_t st) {
+    ttvb_handle* h = pt->h;
+    const ttvb::PTState& S = pt->S;
+    const int half = S.nwalkers / 2;
+    const int64_t B = (int64_t)S.ntemps * half;
+    const int tb = 128, gb = (int)((B + tb - 1) / tb);
+    for (int j = 0; j < 2; j++) {
+        ttvb::pt_propose_kernel<<<gb, tb, 0, st>>>(S, j);
+        int rc = run_batch(h, S.q, B, pt->mode, nullptr, S.qlogl, nullptr, nullptr, 0, nullptr, nullptr, nullptr,
+                           nullptr, nullptr, nullptr, (void*)st);
+        if (rc != TTVB_OK) return rc;
+        ttvb::pt_accept_kernel<<<gb, tb, 0, st>>>(S, j);
+        h->launches += 2;
+    }
+    ttvb::pt_swap_ladder_kernel<<<1, 1024, 0, st>>>(S, pt->hb, adapt, pt->lag, pt->adapt_time);
+    h->launches++;
+    CU(cudaGetLastError());
+    return TTVB_OK;
+}
+
 int ttvb_pt_run(ttvb_pt* pt, int64_t iterations, int adapt, void* stream) {
     if (!pt) return fail(TTVB_E_INVALID, "null argument");
     ttvb_handle* h = pt->h;
     CU(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
-    const ttvb::PTState& S = pt->S;
-    const int half = S.nwalkers / 2;
-    const int64_t B = (int64_t)S.ntemps * half;
-    const int tb = 128, gb = (int)((B + tb - 1) / tb), gw = (S.nwalkers + tb - 1) / tb;
-    for (int64_t n = 0; n < iterations; n++) {
-        for (int j = 0; j < 2; j++) {
-            ttvb::pt_propose_kernel<<<gb, tb, 0, st>>>(S, pt->time, j);
-            int rc = run_batch(h, S.q, B, pt->mode, nullptr, S.qlogl, nullptr, nullptr, 0, nullptr, nullptr, nullptr,
-                               nullptr, nullptr, nullptr, stream);
-            if (rc != TTVB_OK) return rc;
-            ttvb::pt_accept_kernel<<<gb, tb, 0, st>>>(S, pt->time, j);
-            h->launches += 2;
+    const int ai = adapt ? 1 : 0;
+    int64_t n = 0;
+    if (pt->use_graph && iterations >= 3) {
+        // The first iteration runs plainly (it sizes the handle's scratch allocations); the second
+        // is CAPTURED on an internal stream (the caller's may be the legacy default stream, which
+        // cannot be captured) and the graph replayed for all the others. Nothing in an iteration
+        // depends on its number except through the device-side counter, so one graph serves them all.
+        int rc = pt_iteration(pt, adapt, st);
+        if (rc != TTVB_OK) return rc;
+        pt->time++; n++;
+        if (!pt->gs) {
+            CU(cudaStreamCreateWithFlags(&pt->gs, cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&pt->ev_a, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&pt->ev_b, cudaEventDisableTiming));
         }
-        for (int i = S.ntemps - 1; i >= 1; i--) {
-            ttvb::pt_swap_kernel<<<gw, tb, 0, st>>>(S, pt->time, i, pt->hb);
-            h->launches++;
+        CU(cudaEventRecord(pt->ev_a, st));
+        CU(cudaStreamWaitEvent(pt->gs, pt->ev_a, 0));
+        if (!pt->gexec[ai]) {
+            const long long l0 = h->launches;
+            cudaGraph_t graph = nullptr;
+            CU(cudaStreamBeginCapture(pt->gs, cudaStreamCaptureModeRelaxed));
+            h->in_capture = true;
+            rc = pt_iteration(pt, adapt, pt->gs);
+            h->in_capture = false;
+            cudaError_t ce = cudaStreamEndCapture(pt->gs, &graph);
+            if (rc != TTVB_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+            if (ce != cudaSuccess) return fail(TTVB_E_CUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(ce));
+            ce = cudaGraphInstantiate(&pt->gexec[ai], graph, 0);
+            cudaGraphDestroy(graph);
+            if (ce != cudaSuccess) return fail(TTVB_E_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
+            pt->launches_per_iter = h->launches - l0;
+            h->launches = l0;                        // capturing launched nothing
         }
-        ttvb::pt_ladder_kernel<<<1, 32, 0, st>>>(S, pt->time, adapt, pt->lag, pt->adapt_time);
-        h->launches++;
+        for (; n < iterations; n++) {
+            CU(cudaGraphLaunch(pt->gexec[ai], pt->gs));
+            h->launches += pt->launches_per_iter;
+            pt->time++;
+        }
+        CU(cudaEventRecord(pt->ev_b, pt->gs));
+        CU(cudaStreamWaitEvent(st, pt->ev_b, 0));
+        CU(cudaEventRecord(h->ev_done, st));
+        return TTVB_OK;
+    }
+    for (; n < iterations; n++) {
+        int rc = pt_iteration(pt, adapt, st);
+        if (rc != TTVB_OK) return rc;
         pt->time++;
     }
-    CU(cudaGetLastError());
     return TTVB_OK;
 }
 
@@ -722,7 +813,7 @@ int ttvb_pt_half_begin(ttvb_pt* pt, int half, int64_t lo, int64_t hi, void* stre
     CU(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)stream;
     const int tb = 128, gb = (int)((B + tb - 1) / tb);
-    ttvb::pt_propose_kernel<<<gb, tb, 0, st>>>(S, pt->time, half);
+    ttvb::pt_propose_kernel<<<gb, tb, 0, st>>>(S, half);
     h->launches++;
     CU(cudaGetLastError());
     if (hi == lo) return TTVB_OK;
@@ -738,15 +829,11 @@ int ttvb_pt_half_end(ttvb_pt* pt, int half, int adapt, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     const ttvb::PTState& S = pt->S;
     const int64_t B = (int64_t)S.ntemps * (S.nwalkers / 2);
-    const int tb = 128, gb = (int)((B + tb - 1) / tb), gw = (S.nwalkers + tb - 1) / tb;
-    ttvb::pt_accept_kernel<<<gb, tb, 0, st>>>(S, pt->time, half);
+    const int tb = 128, gb = (int)((B + tb - 1) / tb);
+    ttvb::pt_accept_kernel<<<gb, tb, 0, st>>>(S, half);
     h->launches++;
     if (half == 1) {
-        for (int i = S.ntemps - 1; i >= 1; i--) {
-            ttvb::pt_swap_kernel<<<gw, tb, 0, st>>>(S, pt->time, i, pt->hb);
-            h->launches++;
-        }
-        ttvb::pt_ladder_kernel<<<1, 32, 0, st>>>(S, pt->time, adapt, pt->lag, pt->adapt_time);
+        ttvb::pt_swap_ladder_kernel<<<1, 1024, 0, st>>>(S, pt->hb, adapt, pt->lag, pt->adapt_time);
         h->launches++;
         pt->time++;
     }
@@ -822,6 +909,20 @@ int ttvb_selftest_seed_scan(int device, const uint32_t* rcp_tab, const uint32_t*
     mismatches[0] = bad[0]; mismatches[1] = bad[1];
     cudaFree(d_rcp); cudaFree(d_rsq); cudaFree(d_bad); cudaFree(d_first);
     return TTVB_OK;
+}
+
+int ttvb_check_failures(int device, int32_t counts[8]) {
+    if (!counts) return fail(TTVB_E_INVALID, "null argument");
+#ifdef TTVB_CHECKS
+    CU(cudaSetDevice(device));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpyFromSymbol(counts, g_ttvb_check, 8 * sizeof(int)));
+    return TTVB_OK;
+#else
+    (void)device;
+    for (int i = 0; i < 8; i++) counts[i] = -1;
+    return fail(TTVB_E_UNSUPPORTED, "this libttvb was built without -DTTVB_CHECKS");
+#endif
 }
 
 int ttvb_fp64_peak(ttvb_handle* h, double* tflops, float* ms_out) {

@@ -34,6 +34,19 @@
 #define TTVB_RS (TTVB_TPB + 1)
 #define TTVB_ST_BAD_TRANSIT_BIT 4
 
+// Self-checks (compute-sanitizer is not available on the GPU pool, profiles/r2a_compute_sanitizer_closed.txt):
+// a -DTTVB_CHECKS build verifies, on the device, the indices of every queue / ring / result-area /
+// observed-table / event-table access and bounds the inter-CTA waits, counting violations by kind
+// in a device array (read back with ttvb_check_failures). The product build compiles them away.
+#ifdef TTVB_CHECKS
+__device__ int g_ttvb_check[8];
+#define TTVB_CHECK(cond, kind) do { if (!(cond)) atomicAdd(&g_ttvb_check[(kind)], 1); } while (0)
+#else
+#define TTVB_CHECK(cond, kind) do { } while (0)
+#endif
+enum { CHK_QUEUE_SLOT = 0, CHK_BATCH_HEADER = 1, CHK_FOLD = 2, CHK_OBS_INDEX = 3, CHK_TABLE_INDEX = 4, CHK_HANDOVER_WAIT = 5,
+       CHK_UNIT = 6, CHK_KINDS = 8 };
+
 namespace ttvb {
 
 struct DevSys {
@@ -76,6 +89,9 @@ struct DevSys {
     int nseg;
     long long seg_len;        // steps per segment
     int* sched;
+    // streaming input (host-pointer calls): number of rows of `x` uploaded so far, bumped by the
+    // copy stream while the kernel runs; a tile waits until its rows are there. nullptr: all there.
+    const int* ready;
     double* ctx_d;            // [25N+3][ctx_stride]
     int* ctx_i;               // [2N+4][ctx_stride]
     long long ctx_stride;
@@ -170,6 +186,9 @@ __device__ __noinline__ void process_batch(const DevSys& S, int count, WarpQ Q, 
         sl[e] = act[e] ? slot : (lane < count ? lane : 0);     // idle chains shadow a valid event
         const int4 hd = __ldcg(reinterpret_cast<const int4*>(Q.qi) + sl[e]);
         owner[e] = hd.x; planet[e] = hd.y; epoch[e] = hd.z; seq[e] = hd.w;
+        TTVB_CHECK(count >= 1 && count <= CAP && sl[e] >= 0 && sl[e] < count, CHK_QUEUE_SLOT);
+        TTVB_CHECK(owner[e] >= 0 && owner[e] < 32 && planet[e] >= 0 && planet[e] < N && epoch[e] >= 0 && seq[e] >= 0,
+                   CHK_BATCH_HEADER);
         otid[e] = warp_base_tid + owner[e];
         const double* tq = Q.qd + (long long)sl[e] * SD + 18 * N;
         const double2 t01 = __ldcg(reinterpret_cast<const double2*>(tq));
@@ -270,6 +289,7 @@ __device__ __noinline__ void process_batch(const DevSys& S, int count, WarpQ Q, 
             const long long sys = warp_base_sys + owner[e];
             if (seq[e] < S.cap) {
                 const long long o = sys * (long long)S.cap + seq[e];
+                TTVB_CHECK(sys >= 0 && sys < S.B && o >= 0 && o < S.B * (long long)S.cap, CHK_TABLE_INDEX);
                 S.ev_planet[o] = planet[e]; S.ev_epoch[o] = epoch[e];
                 S.ev_time[o] = tt; S.ev_rsky[o] = rs; S.ev_vsky[o] = vs;
             }
@@ -286,6 +306,7 @@ __device__ __noinline__ void process_batch(const DevSys& S, int count, WarpQ Q, 
                 if (obs_epoch_s[m] < epoch[e]) a = m + 1; else b = m;
             }
             pos = a;
+            TTVB_CHECK(pos >= S.obs_start[planet[e]] && pos <= end && end <= S.nobs, CHK_OBS_INDEX);
             if (pos < end && obs_epoch_s[pos] == epoch[e]) {
                 info |= 0x200;
                 const double d = (obs_time_s[pos] - tt) / obs_sigma_s[pos];
@@ -322,12 +343,14 @@ __device__ __forceinline__ void consume_results(int lane, int tid, const int* re
             if (mine != 0u) {
                 const int j = 32 * e + __ffs(mine) - 1;
                 mine &= mine - 1u;
+                TTVB_CHECK(j >= 0 && j < CAP, CHK_FOLD);
                 const int info = res_i[0 * CAP + j];
                 status |= res_i[2 * CAP + j];
                 if (info & 0x100) {
                     const int pl = info & 0xff, pos = res_i[1 * CAP + j];
                     int cur = cur_s[pl * TTVB_TPB + tid];
                     double a = acc_s[pl * TTVB_TPB + tid];
+                    TTVB_CHECK(pl >= 0 && pl < TTVB_MAX_PLANETS_P1 - 1 && cur >= 0 && pos >= 0 && pos - cur <= 100000, CHK_FOLD);
                     while (cur < pos) { a += TTVB_PENALTY; cur++; }
                     if ((info & 0x200) && cur == pos) { a += res_d[j]; cur++; }
                     acc_s[pl * TTVB_TPB + tid] = a;
@@ -442,6 +465,7 @@ __device__ __noinline__ bool run_steps(StepCtx<N>& cx, const double dt, const lo
                             const int b = __ffs(mm) - 1;
                             mm &= mm - 1u;
                             const double* src = hist + (tid - lane + b);
+                            TTVB_CHECK(qcount + taken >= 0 && qcount + taken < TTVB_QCAP && b >= 0 && b < 32, CHK_QUEUE_SLOT);
                             double* dst = qdq + (qcount + taken) * QLayout<N>::SD;
                             taken++;
 #pragma unroll
@@ -451,6 +475,7 @@ __device__ __noinline__ bool run_steps(StepCtx<N>& cx, const double dt, const lo
                     }
                     if (t && rank < room) {
                         const int slot = qcount + rank;
+                        TTVB_CHECK(slot >= 0 && slot < TTVB_QCAP, CHK_QUEUE_SLOT);
                         int ci = 0;
 #pragma unroll
                         for (int j = 0; j < N; j++) if (j == i) { ci = count[j]; count[j] = ci + 1; }
@@ -556,6 +581,7 @@ ttvb_main_kernel(const __grid_constant__ DevSys S) {
         if (unit >= nunits) break;
         const int seg = unit / (int)ntiles;
         const long long tile = unit - (long long)seg * ntiles;
+        TTVB_CHECK(unit >= 0 && seg >= 0 && seg < S.nseg && tile >= 0 && tile < ntiles, CHK_UNIT);
         const long long tile_base = tile * TTVB_TPB;
         const long long sys = tile_base + tid;
         bool alive = sys < S.B;
@@ -570,7 +596,15 @@ ttvb_main_kernel(const __grid_constant__ DevSys S) {
             // ---- resume: wait until the previous segment of this tile is published, reload the context
             if (tid == 0) {
                 volatile int* flag = S.sched + 1 + tile;
+#ifdef TTVB_CHECKS
+                const long long t_start = clock64();
+                while (*flag < seg) {
+                    __nanosleep(256);
+                    if (clock64() - t_start > 20000000000LL) { TTVB_CHECK(false, CHK_HANDOVER_WAIT); break; }
+                }
+#else
                 while (*flag < seg) __nanosleep(256);
+#endif
             }
             __syncthreads();
             __threadfence();
@@ -609,9 +643,31 @@ ttvb_main_kernel(const __grid_constant__ DevSys S) {
         // ---- first segment: coalesced staging of this tile's input rows, prologue
         {
             const long long nrow = (S.B - tile_base < TTVB_TPB) ? (S.B - tile_base) : TTVB_TPB;
+            bool arrived = true;
+            if (S.ready != nullptr) {
+                // streamed input: wait until the copy stream has delivered this tile's rows (rare: the
+                // uploads run ahead of the kernel). A bounded wait, so that a failed upload cannot hang
+                // the GPU: after ~2 s the tile gives up and reports TTVB_ST_INPUT_TIMEOUT.
+                if (tid == 0) {
+                    const int need = (int)(tile_base + nrow);
+                    const long long t_start = clock64();
+                    int ok = 1;
+                    while (*reinterpret_cast<const volatile int*>(S.ready) < need) {
+                        __nanosleep(1000);
+                        if (clock64() - t_start > 4000000000LL) { ok = 0; break; }
+                    }
+                    s_unit = ok ? unit : -1 - unit;
+                }
+                __syncthreads();
+                __threadfence();
+                arrived = s_unit >= 0;
+                if (!arrived) { status |= 32; alive = false; }
+                __syncthreads();
+            }
             const long long nel = nrow * rowlen;
             const double* src = S.x + tile_base * rowlen;
-            for (long long i = tid; i < nel; i += TTVB_TPB) xstage[i] = src[i];
+            if (arrived)
+                for (long long i = tid; i < nel; i += TTVB_TPB) xstage[i] = __ldcg(src + i);
         }
         __syncthreads();
         // ---- prologue: bounds, cube->physical, constants, elements -> Jacobi state

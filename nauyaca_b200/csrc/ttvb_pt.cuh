@@ -87,11 +87,14 @@ struct PTState {
     double* nswap;               // [ntemps]
     double* nswap_acc;
     double* ratios;              // [ntemps-1] swap acceptance of the current iteration
+    long long* time_dev;         // iteration counter ON THE DEVICE: every kernel reads it from here, so that
+                                 // one iteration is the same work whatever its number (CUDA-graph replay)
     uint32_t seed0, seed1;
 };
 
 // stretch proposals of half `j` at iteration `it`
-__global__ void pt_propose_kernel(PTState S, long long it, int j) {
+__global__ void pt_propose_kernel(PTState S, int j) {
+    const long long it = *S.time_dev;
     const int half = S.nwalkers / 2;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= S.ntemps * half) return;
@@ -111,7 +114,8 @@ __global__ void pt_propose_kernel(PTState S, long long it, int j) {
 }
 
 // accept / reject the proposals of half `j`
-__global__ void pt_accept_kernel(PTState S, long long it, int j) {
+__global__ void pt_accept_kernel(PTState S, int j) {
+    const long long it = *S.time_dev;
     const int half = S.nwalkers / 2;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= S.ntemps * half) return;
@@ -137,39 +141,40 @@ __global__ void pt_accept_kernel(PTState S, long long it, int j) {
     if (acc) S.nprop_acc[wi] += 1.0;
 }
 
-// temperature swap between chains i and i-1 (one launch per pair, hottest first)
-__global__ void pt_swap_kernel(PTState S, long long it, int i, int hb) {
-    const int w = blockIdx.x * blockDim.x + threadIdx.x;
-    __shared__ int s_acc;
-    if (threadIdx.x == 0) s_acc = 0;
-    __syncthreads();
-    if (w < S.nwalkers) {
-        const uint32_t k0 = S.seed0 ^ (uint32_t)(it * 2654435761u), k1 = S.seed1 + (uint32_t)(it >> 32);
-        const uint32_t a = feistel_perm((uint32_t)w, (uint32_t)S.nwalkers, hb, k0, k1 ^ (uint32_t)(2 * i));
-        const uint32_t b = feistel_perm((uint32_t)w, (uint32_t)S.nwalkers, hb, k0, k1 ^ (uint32_t)(2 * i + 1));
-        uint32_t o[4];
-        Philox::gen((uint32_t)w, (uint32_t)it, PT_RNG_SWAP, (uint32_t)i, S.seed0, S.seed1, o);
-        const double dbeta = S.betas[i - 1] - S.betas[i];
-        const int ia = i * S.nwalkers + (int)a, ib = (i - 1) * S.nwalkers + (int)b;
-        const double la = S.logl[ia], lb = S.logl[ib];
-        const double paccept = dbeta * (la - lb);
-        if (paccept > log(Philox::u01(o[0], o[1]))) {
-            double* pa = S.p + (size_t)ia * S.dim;
-            double* pb = S.p + (size_t)ib * S.dim;
-            for (int d = 0; d < S.dim; d++) { const double tmp = pa[d]; pa[d] = pb[d]; pb[d] = tmp; }
-            S.logl[ia] = lb;
-            S.logl[ib] = la;
-            atomicAdd(&s_acc, 1);
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0 && s_acc) atomicAdd(S.ratios + (i - 1), (double)s_acc);
-}
-
-// bookkeeping after the swaps of one iteration, then the ladder adaptation (one thread)
-__global__ void pt_ladder_kernel(PTState S, long long time, int adapt, double lag, double adapt_time) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+// Temperature swaps of one iteration (chains i and i-1, hottest pair first), the swap bookkeeping,
+// the ladder adaptation and the advance of the iteration counter: ONE block. The pairs of a level
+// are disjoint (two permutations of the walkers), the levels are separated by block barriers.
+__global__ void __launch_bounds__(1024) pt_swap_ladder_kernel(PTState S, int hb, int adapt, double lag, double adapt_time) {
+    const long long it = *S.time_dev;
     const int nt = S.ntemps;
+    __shared__ int s_acc;
+    for (int i = nt - 1; i >= 1; i--) {
+        if (threadIdx.x == 0) s_acc = 0;
+        __syncthreads();
+        const uint32_t k0 = S.seed0 ^ (uint32_t)(it * 2654435761u), k1 = S.seed1 + (uint32_t)(it >> 32);
+        const double dbeta = S.betas[i - 1] - S.betas[i];
+        for (int w = threadIdx.x; w < S.nwalkers; w += blockDim.x) {
+            const uint32_t a = feistel_perm((uint32_t)w, (uint32_t)S.nwalkers, hb, k0, k1 ^ (uint32_t)(2 * i));
+            const uint32_t b = feistel_perm((uint32_t)w, (uint32_t)S.nwalkers, hb, k0, k1 ^ (uint32_t)(2 * i + 1));
+            uint32_t o[4];
+            Philox::gen((uint32_t)w, (uint32_t)it, PT_RNG_SWAP, (uint32_t)i, S.seed0, S.seed1, o);
+            const int ia = i * S.nwalkers + (int)a, ib = (i - 1) * S.nwalkers + (int)b;
+            const double la = S.logl[ia], lb = S.logl[ib];
+            const double paccept = dbeta * (la - lb);
+            if (paccept > log(Philox::u01(o[0], o[1]))) {
+                double* pa = S.p + (size_t)ia * S.dim;
+                double* pb = S.p + (size_t)ib * S.dim;
+                for (int d = 0; d < S.dim; d++) { const double tmp = pa[d]; pa[d] = pb[d]; pb[d] = tmp; }
+                S.logl[ia] = lb;
+                S.logl[ib] = la;
+                atomicAdd(&s_acc, 1);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) S.ratios[i - 1] = (double)s_acc;
+        __syncthreads();
+    }
+    if (threadIdx.x != 0) return;
     for (int i = nt - 1; i >= 1; i--) {
         const double nacc = S.ratios[i - 1];
         S.nswap[i] += S.nwalkers; S.nswap[i - 1] += S.nwalkers;
@@ -177,7 +182,7 @@ __global__ void pt_ladder_kernel(PTState S, long long time, int adapt, double la
         S.ratios[i - 1] = nacc / S.nwalkers;
     }
     if (adapt && nt > 2) {
-        const double decay = lag / ((double)time + lag);
+        const double decay = lag / ((double)it + lag);
         const double kappa = decay / adapt_time;
         // deltaTs = diff(1/betas[:-1]) * exp(kappa (ratios[:-1] - ratios[1:])); betas[1:-1] = 1/(cumsum + 1/betas[0])
         double cum = 1.0 / S.betas[0];
@@ -191,6 +196,7 @@ __global__ void pt_ladder_kernel(PTState S, long long time, int adapt, double la
         }
     }
     for (int i = 0; i < nt - 1; i++) S.ratios[i] = 0.0;
+    *S.time_dev = it + 1;
 }
 
 }  // namespace ttvb

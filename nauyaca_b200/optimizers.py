@@ -2,13 +2,19 @@
 
 ``Optimizers.run`` starts ``nsols`` independent DE -> Powell -> Nelder-Mead chains, one
 process each (optimizers.py:185-189); every chain calls ``calculate_chi2`` one vector at a
-time, so the reference evaluates at most ``cores`` vectors concurrently. Here the SAME scipy
-calls (same algorithms, same options as optimizers.py:78-113) run one per Python thread, and
-their objective calls meet in a *rendezvous*: all pending vectors are evaluated in ONE
-``ttvb_loglike`` batch, as soon as the coordinator is free (default) or whenever every live chain
-is waiting for a value (``greedy=False``). A DE generation
-(vectorised scipy objective) contributes 30*ndim vectors per chain, Powell and Nelder-Mead
-one vector per chain and round.
+time, so the reference evaluates at most ``cores`` vectors concurrently. Two ways to run the
+chains on the batched objective (``de_pw_nm(method=...)``):
+
+``"lockstep"`` (default): the DE generation of every chain in one batch (30*ndim vectors per
+chain), then Powell and Nelder-Mead of ALL chains advanced together (lockstep.py): each move
+of the search is one ``ttvb_loglike`` batch over the live chains, with the reference's options
+and stopping rules per chain.
+
+``"scipy"``: the SAME scipy calls as optimizers.py:78-113, one per Python thread, their objective
+calls meeting in a *rendezvous*: all pending vectors are evaluated in one batch, as soon as the
+coordinator is free (default) or whenever every live chain is waiting for a value
+(``greedy=False``). Same search path as the serial reference for the same seeds, but Powell and
+Nelder-Mead contribute one vector per chain and round and the host work is serial Python.
 
 ``write_opt_files`` writes the two result tables in the reference's own text layout
 (optimizers.py:122-136, 160-168; utils.writefile :1222) so that ``MCMC(opt_data=np.genfromtxt(
@@ -138,18 +144,47 @@ def _chain(PSystem_bounds, ndim, evaluate, seed, de_opts, powell_opts, nm_opts, 
         batcher.worker_done()
 
 
+def _de_only(PSystem_bounds, evaluate, seed, de_opts, out, idx, batcher):
+    """The differential-evolution stage of one chain (optimizers.py:78-83)."""
+    from scipy.optimize import differential_evolution
+    try:
+        lo = np.array([b[0] for b in PSystem_bounds]); hi = np.array([b[1] for b in PSystem_bounds])
+
+        def f_vec(x):
+            x = np.asarray(x)
+            X = np.atleast_2d(x) if x.ndim == 1 else np.ascontiguousarray(x.T)
+            inside = np.all((X >= lo) & (X <= hi), axis=1)
+            f = np.full(X.shape[0], np.inf)
+            if inside.any():
+                f[inside] = evaluate(X[inside])
+            return float(f[0]) if x.ndim == 1 else f
+        de = differential_evolution(f_vec, list(zip(lo, hi)), seed=seed, vectorized=True, updating="deferred", **de_opts)
+        out[idx] = (np.asarray(de.x, dtype=np.float64), float(de.fun))
+    except BaseException as e:
+        out[idx] = e
+    finally:
+        batcher.worker_done()
+
+
 def de_pw_nm(PSystem, nsols, seed=None, evaluate=None, powell=True, de_opts=None, powell_opts=None, nm_opts=None,
-             greedy=True):
-    """``nsols`` DE -> Powell -> Nelder-Mead chains in lock-step batches.
+             greedy=True, method="lockstep"):
+    """``nsols`` DE -> Powell -> Nelder-Mead chains on the batched objective.
 
     Returns a list of ``[f, x_cube(list), x_phys(list)]`` like ``Optimizers.DE_PW_NM``
     (optimizers.py:46-139), in chain order, plus the batch-size log as second value.
-    evaluate: X[B, ndim] -> chi2[B] on cube vectors (default: the GPU engine of PSystem with the
-    full unit hypercube; each chain applies its own, shrunken, bounds on the host)."""
+    evaluate: X[B, ndim] -> chi2[B] on cube vectors (default: a private GPU engine of PSystem with the
+    full unit hypercube; each chain applies its own, shrunken, bounds on the host).
+    method: "lockstep" (default) - the DE generations of all chains in one batch each, then Powell
+    and Nelder-Mead of all chains advanced together (nauyaca_b200/lockstep.py: every move of the
+    search is ONE batch over the live chains); "scipy" - the reference's own scipy calls, one
+    chain per thread, their objective calls meeting in rendezvous batches (same search path as
+    the serial reference for the same seeds; an order of magnitude more launches)."""
     ndim = PSystem.ndim
+    own_engine = None
     if evaluate is None:
-        eng = _u.engine_for(PSystem)
-        eng.set_cube_bounds([[0.0, 1.0]] * ndim)
+        from .engine import BatchEngine
+        own_engine = eng = BatchEngine(PSystem, device=_u.DEFAULT_DEVICE)     # private: its cube bounds are the unit
+        eng.set_cube_bounds([[0.0, 1.0]] * ndim)                              # hypercube, whatever PSystem.hypercube is
 
         def evaluate(X):
             return eng.loglike(np.ascontiguousarray(X), mode=0)[0]
@@ -159,30 +194,68 @@ def de_pw_nm(PSystem, nsols, seed=None, evaluate=None, powell=True, de_opts=None
     pw_o.update(powell_opts or {})
     nm_o = dict(maxiter=15000, maxfev=15000, xatol=0.0001, fatol=1, disp=False, adaptive=True)
     nm_o.update(nm_opts or {})
-    batcher = RendezvousBatcher(evaluate, nsols, greedy=greedy)
-    out = [None] * nsols
     ss = np.random.SeedSequence(seed)
     seeds = [int(s.generate_state(1)[0]) for s in ss.spawn(nsols)]
-    threads = [threading.Thread(target=_chain, daemon=True,
-                                args=([list(h) for h in PSystem.hypercube], ndim, batcher.evaluate, seeds[i], de_o,
-                                      pw_o if powell else None, nm_o, out, i, batcher)) for i in range(nsols)]
-    for t in threads:
-        t.start()
-    batcher.serve()
-    for t in threads:
-        t.join()
-    for r in out:
-        if isinstance(r, BaseException):
-            raise r
-    X = np.stack([r[3] for r in out])
-    phys = None
+    hyper = [list(h) for h in PSystem.hypercube]
     try:
-        flat, _ = _u.engine_for(PSystem).cube_to_physical(X)
-        phys = [list(_u._remove_constants(PSystem, row)) for row in flat]
-    except Exception:
-        phys = [None] * nsols
+        if method == "scipy":
+            batcher = RendezvousBatcher(evaluate, nsols, greedy=greedy)
+            out = [None] * nsols
+            threads = [threading.Thread(target=_chain, daemon=True,
+                                        args=(hyper, ndim, batcher.evaluate, seeds[i], de_o,
+                                              pw_o if powell else None, nm_o, out, i, batcher)) for i in range(nsols)]
+            for t in threads:
+                t.start()
+            batcher.serve()
+            for t in threads:
+                t.join()
+            for r in out:
+                if isinstance(r, BaseException):
+                    raise r
+            batches = batcher.batches
+        elif method == "lockstep":
+            from . import lockstep
+            # DE: one thread per chain, every generation of all chains in one batch
+            batcher = RendezvousBatcher(evaluate, nsols, greedy=False)
+            de = [None] * nsols
+            threads = [threading.Thread(target=_de_only, daemon=True, args=(hyper, batcher.evaluate, seeds[i], de_o, de, i, batcher))
+                       for i in range(nsols)]
+            for t in threads:
+                t.start()
+            batcher.serve()
+            for t in threads:
+                t.join()
+            for r in de:
+                if isinstance(r, BaseException):
+                    raise r
+            x0 = np.stack([r[0] for r in de]); f0 = np.array([r[1] for r in de])
+            # optimizers.py:90: shrink the hypercube around the DE solution for the local stages
+            lo, hi = np.maximum(0.0, x0 - 0.3), np.minimum(1.0, x0 + 0.3)
+            batches = list(batcher.batches)
+            x1, f1 = x0, f0
+            if powell:
+                po = lockstep.powell(evaluate, x0, lo, hi, f0=f0, xtol=pw_o["xtol"], ftol=pw_o["ftol"],
+                                     maxiter=pw_o["maxiter"], maxfev=pw_o["maxfev"])
+                x1, f1 = po["x"], po["fun"]
+                batches += po["batches"]
+            nm = lockstep.nelder_mead(evaluate, x1, lo, hi, xatol=nm_o["xatol"], fatol=nm_o["fatol"], maxiter=nm_o["maxiter"],
+                                      maxfev=nm_o["maxfev"], adaptive=nm_o["adaptive"])
+            batches += nm["batches"]
+            out = [(float(f0[i]), float(f1[i]), float(nm["fun"][i]), nm["x"][i].copy()) for i in range(nsols)]
+        else:
+            raise ValueError("method must be 'lockstep' or 'scipy'")
+        X = np.stack([r[3] for r in out])
+        phys = None
+        try:
+            flat, _ = _u.engine_for(PSystem).cube_to_physical(X)
+            phys = [list(_u._remove_constants(PSystem, row)) for row in flat]
+        except Exception:
+            phys = [None] * nsols
+    finally:
+        if own_engine is not None:
+            own_engine.close()
     results = [[out[i][2], X[i].tolist(), phys[i]] for i in range(nsols)]
-    return results, {"batches": batcher.batches, "stages": [(r[0], r[1], r[2]) for r in out]}
+    return results, {"batches": batches, "stages": [(r[0], r[1], r[2]) for r in out]}
 
 
 def run_optimizers(PSystem, nsols=1, seed=None, **kw):

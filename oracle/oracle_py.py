@@ -36,9 +36,15 @@ class _Sys(C.Structure):
 
 _lib = None
 _lib_native = None
+_lib_lock = __import__("threading").Lock()
 
 
 def lib(native=False):
+    with _lib_lock:
+        return _lib_locked(native)
+
+
+def _lib_locked(native=False):
     """The oracle library. native=True: the timing build (host divide/sqrt instead of the
     emulated GPU seeds; last-bit differences) that bench.py's CPU legs time - never the checker."""
     global _lib, _lib_native

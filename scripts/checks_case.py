@@ -1,6 +1,8 @@
-"""Small invocations of the hot path for compute-sanitizer (memcheck / racecheck / synccheck).
+"""The cases a compute-sanitizer run would cover, for the SELF-CHECKING kernel build
+(-DTTVB_CHECKS, nauyaca_b200/libttvb_checks.so; compute-sanitizer itself is closed on the GPU pool,
+profiles/r2a_compute_sanitizer_closed.txt):
 
-    TTVB_NSEG=3 compute-sanitizer --tool racecheck python scripts/sanitize_case.py
+    TTVB_LIB=nauyaca_b200/libttvb_checks.so TTVB_NSEG=3 python scripts/checks_case.py
 
 Case A: C4-shaped batch (3 planets, near-mode walkers) cut into 3 time segments, so that the
         inter-CTA hand-over (context save, per-tile flag, resume) runs.
@@ -26,11 +28,13 @@ spec = systems["sys3"]
 osys = oracle_py.OracleSystem(spec)
 eng = nb.BatchEngine(spec)
 rng = np.random.default_rng(3)
-nA = int(os.environ.get("SAN_NA", "640"))
+nA = int(os.environ.get("CHK_NA", "40000"))     # more than one wave of tiles: units are handed between CTAs
 XA = rng.random((nA, spec["ndim"]))
 chi2, logl, st = eng.loglike(XA, mode=0)
-o = osys.loglike(XA, mode=0)
-assert np.array_equal(chi2, o[0]) and np.array_equal(st, o[2]), "case A mismatch"
+o = osys.loglike_threads(XA[:2000], mode=0)
+assert np.array_equal(chi2[:2000], o[0]) and np.array_equal(st[:2000], o[2]), "case A mismatch"
+sub = rng.permutation(nA)[:3000]
+assert np.array_equal(eng.loglike(XA[sub], mode=0)[0], chi2[sub]), "case A: position dependence"
 XB = np.repeat(rng.random((1, spec["ndim"])), 256, axis=0)
 chi2, logl, st = eng.loglike(XB, mode=0)
 o = osys.loglike(XB[:1], mode=0)
@@ -46,4 +50,9 @@ smp = DeviceSampler(e2, nwalkers=32, ntemps=3, seed=5)
 p0 = 0.45 + 0.1 * rng.random((3, 32, doc["ndim"]))
 for _ in smp.sample(p0, iterations=3, adapt=True):
     pass
-print("sanitize_case ok: launches", eng.launch_count() + e2.launch_count())
+import ctypes  # noqa: E402
+from nauyaca_b200 import _lib  # noqa: E402
+counts = (ctypes.c_int32 * 8)()
+rc = _lib.lib().ttvb_check_failures(0, counts)
+print(json.dumps({"checks_case": "ok", "launches": eng.launch_count() + e2.launch_count(), "check_rc": rc,
+                  "violations": list(counts), "nseg": os.environ.get("TTVB_NSEG"), "lib": os.path.basename(_lib.LIB_PATH)}))

@@ -259,3 +259,18 @@ def test_physical_mode_bounds(oracle):
     _same(r[0], o[0]); _same(r[1], o[1]); _same(r[2], o[2])
     assert r[2][5] & 1 and r[2][6] & 1 and not (r[2][7] & 1) and not (r[2][8] & 1)
     eng.close()
+
+
+def test_two_engines_of_different_table_size_share_a_kernel(systems, oracle):
+    """The dynamic shared-memory limit is a property of the kernel function, not of a handle: creating
+    a second engine with a smaller observed table (here: none, as utils.run_TTVFast does) must not
+    break the launches of the first."""
+    import nauyaca_b200 as nb
+    spec = systems["sys3f"]
+    big = nb.BatchEngine(spec)
+    X = np.random.default_rng(3).random((8, spec["ndim"]))
+    ref = big.loglike(X, mode=0)[0]
+    raw = nb.utils._raw_engine(3, spec["mstar"], spec["t0"], spec["ftime"], spec["dt"])
+    raw.ephemeris(oracle.OracleSystem(spec).cube_to_physical(X[0])[None, :], mode=2)
+    assert np.array_equal(big.loglike(X, mode=0)[0], ref)
+    big.close()

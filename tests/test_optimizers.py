@@ -70,13 +70,13 @@ def test_chains_equal_serial_scipy_and_are_batched():
     from scipy.optimize import differential_evolution, minimize
     PS = _PS(4)
     nsols = 6
-    res, info = de_pw_nm(PS, nsols, seed=123, evaluate=_rosen_like,
+    res, info = de_pw_nm(PS, nsols, seed=123, evaluate=_rosen_like, method="scipy",
                          powell_opts={"maxfev": 400}, nm_opts={"maxfev": 600}, greedy=False)
     assert max(info["batches"]) == nsols * 30 * 4                     # a DE generation of every chain at once
     assert np.median(info["batches"]) >= 2
     # the greedy policy (default: a batch leaves as soon as the coordinator is free) groups the same
     # evaluations differently and returns the same chains
-    res_g, info_g = de_pw_nm(PS, nsols, seed=123, evaluate=_rosen_like,
+    res_g, info_g = de_pw_nm(PS, nsols, seed=123, evaluate=_rosen_like, method="scipy",
                              powell_opts={"maxfev": 400}, nm_opts={"maxfev": 600})
     assert sum(info_g["batches"]) == sum(info["batches"])
     assert all(a[0] == b[0] and a[1] == b[1] for a, b in zip(res, res_g))
@@ -98,6 +98,43 @@ def test_chains_equal_serial_scipy_and_are_batched():
                       options=dict(maxiter=15000, maxfev=600, xatol=0.0001, fatol=1, disp=False, adaptive=True))
         assert info["stages"][i] == (de.fun, po.fun, nm.fun)
         assert res[i][0] == nm.fun and res[i][1] == list(nm.x)
+
+
+def test_lockstep_local_search_matches_scipy_in_quality():
+    """Powell and Nelder-Mead of all chains advanced together (lockstep.py): every move is one batch over
+    the live chains, the stopping rules are scipy's, and the minima are as good as those of the serial
+    scipy chains on the same objective."""
+    from scipy.optimize import minimize
+    from nauyaca_b200 import lockstep
+    n, C = 5, 12
+    rng = np.random.default_rng(7)
+    x0 = 0.5 + 0.15 * rng.standard_normal((C, n))
+    lo, hi = np.maximum(0, x0 - .3), np.minimum(1, x0 + .3)
+    calls = []
+
+    def ev(X):
+        calls.append(X.shape[0])
+        return _rosen_like(X)
+    po = lockstep.powell(ev, x0, lo, hi)
+    assert np.all(po["fun"] <= _rosen_like(x0)) and np.all((po["x"] >= lo) & (po["x"] <= hi))
+    assert max(calls) >= C * 8                                   # a comb of all chains in one batch
+    nm = lockstep.nelder_mead(ev, po["x"], lo, hi)
+    assert np.all(nm["fun"] <= po["fun"]) and np.all((nm["x"] >= lo) & (nm["x"] <= hi))
+    assert np.all(nm["nfev"] <= 15000) and np.all(nm["nit"] >= 1)
+    ref = []
+    for c in range(C):
+        def f(x, c=c):
+            x = np.asarray(x)
+            return float(_rosen_like(x[None, :])[0]) if np.all((x >= lo[c]) & (x <= hi[c])) else np.inf
+        p = minimize(f, list(x0[c]), method="Powell", options=dict(maxiter=12000, maxfev=12000, xtol=0.001, ftol=1))
+        q = minimize(f, list(p.x), method="Nelder-Mead", options=dict(maxiter=15000, maxfev=15000, xatol=1e-4, fatol=1, adaptive=True))
+        ref.append(q.fun)
+    # same stopping rule (fatol = 1): both end within a few units of the minimum of the box
+    assert np.median(nm["fun"]) <= np.median(ref) + 1.0 and np.max(nm["fun"] - np.array(ref)) < 5.0
+    # the whole driver: DE generations batched over the chains, then the lock-step stages
+    res, info = de_pw_nm(_PS(4), 6, seed=5, evaluate=_rosen_like)
+    assert len(res) == 6 and all(s[2] <= s[1] <= s[0] for s in info["stages"])
+    assert max(info["batches"]) == 6 * 30 * 4 and np.median(info["batches"]) >= 6
 
 
 def test_opt_files_have_the_reference_layout(tmp_path):
