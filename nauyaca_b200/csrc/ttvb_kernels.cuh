@@ -398,13 +398,19 @@ __device__ __noinline__ bool run_steps(StepCtx<N>& cx, const double dt, const lo
     long long k = cx.k;
     bool full = false;
     constexpr int CPR = (12 * N + 31) / 32;
+    // ONE warp reduction per step tells both what the push phase and the loop head need to know:
+    // bits 0..N-1 = planets that triggered in some lane, bit 31 = some lane still has a live system.
+    // It is issued right after the trigger check of a step and consumed after the arithmetic of the
+    // next one, so its latency is hidden (a superset of the planets is harmless: the per-planet
+    // ballot of the push phase then comes back empty).
+    unsigned warp_state = __reduce_or_sync(0xffffffffu, (unsigned)trigmask | (alive ? 0x80000000u : 0u));
     // a call that comes back from a refinement in the middle of a push phase re-enters there
     if (pending) { pending = false; goto push_phase; }
 #pragma unroll 1
     for (;;) {
         {
             if (k > k1) break;
-            if (__ballot_sync(0xffffffffu, alive) == 0u) break;
+            if (!(warp_state & 0x80000000u)) break;
             {
                 // every lane steps; one without a live system computes on whatever its registers
                 // hold, on the straight-line path (idle flag), and nothing of it is ever used
@@ -426,7 +432,7 @@ __device__ __noinline__ bool run_steps(StepCtx<N>& cx, const double dt, const lo
         // ---- push the events triggered at step k-1 (they now have p_{k-2}, p_{k-1}, p_k). The two
         //      older states are in the ring: all 32 lanes copy them together, one field each; the
         //      owner adds p_k from its registers and the header.
-        unsigned pm = __reduce_or_sync(0xffffffffu, (unsigned)trigmask);     // planets that triggered somewhere in the warp
+        unsigned pm = warp_state & 0x7fffffffu;                               // planets that triggered somewhere in the warp
         if (pm != 0u) {
             __syncwarp();
             const unsigned long long pol = q_policy();
@@ -450,54 +456,54 @@ __device__ __noinline__ bool run_steps(StepCtx<N>& cx, const double dt, const lo
                     cp_dst[r] = e;
                 }
             }
-            while (pm != 0u && !full) {
-                const int i = __ffs(pm) - 1;
-                pm &= pm - 1u;
-                bool t = (trigmask >> i) & 1;
-                unsigned m = __ballot_sync(0xffffffffu, t);
-                while (m) {
-                    const int room = TTVB_QCAP - qcount;
-                    const int rank = __popc(m & ((1u << lane) - 1u));
-                    {
-                        unsigned mm = m;
-                        int taken = 0;
-                        while (mm != 0u && taken < room) {
-                            const int b = __ffs(mm) - 1;
-                            mm &= mm - 1u;
-                            const double* src = hist + (tid - lane + b);
-                            TTVB_CHECK(qcount + taken >= 0 && qcount + taken < TTVB_QCAP && b >= 0 && b < 32, CHK_QUEUE_SLOT);
-                            double* dst = qdq + (qcount + taken) * QLayout<N>::SD;
-                            taken++;
+            // rounds over the LANES that still hold an untold event (usually one round: a lane
+            // rarely triggers for two planets in one step). Per round: the ring states of every such
+            // lane are copied by the whole warp, then all owners store their part side by side. A
+            // lane tells its events in ascending planet order, so the per-system order of the
+            // events (and of the chi2 sum) is the reference's.
+            unsigned evl = __ballot_sync(0xffffffffu, trigmask != 0);
+            while (evl != 0u) {
+                const int room = TTVB_QCAP - qcount;
+                const int rank = __popc(evl & ((1u << lane) - 1u));
+                {
+                    unsigned mm = evl;
+                    int taken = 0;
+                    while (mm != 0u && taken < room) {
+                        const int b = __ffs(mm) - 1;
+                        mm &= mm - 1u;
+                        const double* src = hist + (tid - lane + b);
+                        TTVB_CHECK(qcount + taken >= 0 && qcount + taken < TTVB_QCAP && b >= 0 && b < 32, CHK_QUEUE_SLOT);
+                        double* dst = qdq + (qcount + taken) * QLayout<N>::SD;
+                        taken++;
 #pragma unroll
-                            for (int r = 0; r < CPR; r++)
-                                if (cp_ok[r]) q_st(dst + cp_dst[r], src[cp_src[r]], pol);
-                        }
+                        for (int r = 0; r < CPR; r++)
+                            if (cp_ok[r]) q_st(dst + cp_dst[r], src[cp_src[r]], pol);
                     }
-                    if (t && rank < room) {
-                        const int slot = qcount + rank;
-                        TTVB_CHECK(slot >= 0 && slot < TTVB_QCAP, CHK_QUEUE_SLOT);
-                        int ci = 0;
-#pragma unroll
-                        for (int j = 0; j < N; j++) if (j == i) { ci = count[j]; count[j] = ci + 1; }
-                        q_st4(qi + 4 * slot, lane, i, ci, nev, pol);
-                        nev++;
-                        double* qd = qdq + slot * QLayout<N>::SD + 2 * 6 * N;
-#pragma unroll
-                        for (int j = 0; j < N; j++) {
-                            q_st2(qd + j * 6 + 0, p.x[j][0], p.x[j][1], pol);
-                            q_st2(qd + j * 6 + 2, p.x[j][2], p.v[j][0], pol);
-                            q_st2(qd + j * 6 + 4, p.v[j][1], p.v[j][2], pol);
-                        }
-                        q_st2(qd + 6 * N, Tm2, Tm1, pol);
-                        q_st(qd + 6 * N + 2, Time, pol);
-                        t = false;
-                        trigmask &= ~(1 << i);
-                    }
-                    const int np = __popc(m);
-                    qcount += (np < room) ? np : room;
-                    if (qcount == TTVB_QCAP) { full = true; break; }
-                    m = __ballot_sync(0xffffffffu, t);
                 }
+                if (trigmask != 0 && rank < room) {
+                    const int i = __ffs(trigmask) - 1;
+                    const int slot = qcount + rank;
+                    TTVB_CHECK(slot >= 0 && slot < TTVB_QCAP && i < N, CHK_QUEUE_SLOT);
+                    int ci = 0;
+#pragma unroll
+                    for (int j = 0; j < N; j++) if (j == i) { ci = count[j]; count[j] = ci + 1; }
+                    q_st4(qi + 4 * slot, lane, i, ci, nev, pol);
+                    nev++;
+                    double* qd = qdq + slot * QLayout<N>::SD + 2 * 6 * N;
+#pragma unroll
+                    for (int j = 0; j < N; j++) {
+                        q_st2(qd + j * 6 + 0, p.x[j][0], p.x[j][1], pol);
+                        q_st2(qd + j * 6 + 2, p.x[j][2], p.v[j][0], pol);
+                        q_st2(qd + j * 6 + 4, p.v[j][1], p.v[j][2], pol);
+                    }
+                    q_st2(qd + 6 * N, Tm2, Tm1, pol);
+                    q_st(qd + 6 * N + 2, Time, pol);
+                    trigmask &= trigmask - 1;
+                }
+                const int np = __popc(evl);
+                qcount += (np < room) ? np : room;
+                if (qcount == TTVB_QCAP) { full = true; break; }
+                evl = __ballot_sync(0xffffffffu, trigmask != 0);
             }
             __syncwarp();
             if (full) { pending = true; break; }   // come back to the push phase of this step
@@ -511,6 +517,7 @@ __device__ __noinline__ bool run_steps(StepCtx<N>& cx, const double dt, const lo
                 prev_dot[i] = cd;
             }
         }
+        warp_state = __reduce_or_sync(0xffffffffu, (unsigned)trigmask | (alive ? 0x80000000u : 0u));
         k++;
     }
     cx.p = p;

@@ -573,10 +573,34 @@ static double sky_gp(double mu, const double *x, const double *v, double *rs2_ou
 
 long ttvo_locate_evals;      /* diagnostics: Kepler drifts spent in locate_side */
 
-/* Newton on g(tau)=x.vx+y.vy=0 along the two-body orbit through (x0,v0); returns status.
- * Stops when the step taken is below 1e-7 d: Newton converges quadratically here
- * (|g''/2g'| < 1/d), so the iterate it has just moved to is within 1e-14 d of the root. */
-#define TTVO_TR_TOL 1e-7
+/* One step of the root search of g = x vx + y vy along a two-body orbit: Newton's step d = -g/g'
+ * and its Halley correction d (1 - d g''/(2 g')), with
+ *   g'  = vs^2 - mu rs^2 / r^3 ,   g'' = mu/r^3 ( 3 rs^2 (r.v)/r^2 - 4 g )
+ * (rs^2 = x^2+y^2, vs^2 = vx^2+vy^2). Returns the corrected step, *d_newton the plain one. */
+static double sky_step(double mu, const double *x, const double *v, double *d_newton, double *rs2_out, double *vs2_out)
+{
+    double g = sky_g(x, v);
+    double u = dot3(x, v);
+    double rs2 = fma(x[1], x[1], x[0] * x[0]);
+    double vs2 = fma(v[1], v[1], v[0] * v[0]);
+    double r2 = fma(x[2], x[2], rs2);
+    double ir = rsqrt_fast(r2);
+    double ir2 = ir * ir;
+    double m3 = mu * (ir2 * ir);
+    double gp = fma(-m3, rs2, vs2);
+    double igp = rcp_fast(gp);
+    double d = -g * igp;
+    double gpp = m3 * fma(3.0, rs2 * u * ir2, -4.0 * g);
+    double c = gpp * igp * d;
+    *d_newton = d; *rs2_out = rs2; *vs2_out = vs2;
+    return fma(-0.5 * c, d, d);
+}
+
+/* Root of g(tau) = 0 along the two-body orbit through (x0,v0); returns status. The search stops
+ * when the NEWTON step is below 1e-4 d: the Halley-corrected iterate it then moves to is within
+ * ~1e-13 d of the root (cubic convergence, |d| is 7e-5 d at most after the Hermite first guess
+ * at dt = 0.35 d), so one Kepler drift per side is the rule. */
+#define TTVO_TR_TOL 1e-4
 static int locate_side(double mu, const double *x0, const double *v0, double *tau,
                        double *rsky, double *vsky)
 {
@@ -585,11 +609,9 @@ static int locate_side(double mu, const double *x0, const double *v0, double *ta
         double x[3] = {x0[0], x0[1], x0[2]}, v[3] = {v0[0], v0[1], v0[2]};
         if (kepler_drift(mu, t, x, v)) return ST_BAD_TRANSIT;
         ttvo_locate_evals++;
-        double g = sky_g(x, v);
-        double rs2, vs2;
-        double gp = sky_gp(mu, x, v, &rs2, &vs2);
-        double d = -g * rcp_fast(gp);
-        t = t + d;
+        double d, rs2, vs2;
+        double dh = sky_step(mu, x, v, &d, &rs2, &vs2);
+        t = t + dh;
         if (fabs(d) <= TTVO_TR_TOL) {
             *tau = t; *rsky = sqrt(rs2); *vsky = sqrt(vs2);
             return 0;
