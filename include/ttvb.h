@@ -154,6 +154,14 @@ int ttvb_last_kernel_ms(ttvb_handle *h, float *ms);
 /* Number of kernels launched by this handle since creation (bench.py "gpu_launches"). */
 int ttvb_launch_count(const ttvb_handle *h, int64_t *count);
 
+/* Host-pointer calls of two waves or more are STREAMED: the kernel starts at once and its tiles wait,
+ * on the device, for rows that the copy stream uploads meanwhile. Where uploads cannot run under a
+ * kernel (a profiler serialising the GPU, CUDA_LAUNCH_BLOCKING=1) the tiles give up after a bounded
+ * wait (~0.3 s), the launch is run again on the rows that have arrived by then (same results) and
+ * streaming is switched off for the handle. `count` = launches that were run again. TTVB_NO_STREAM=1
+ * in the environment switches streaming off from the start. */
+int ttvb_stream_retries(const ttvb_handle *h, int64_t *count);
+
 /* FP64 FMA-chain microbenchmark on the handle's device: achieved TFLOP/s (2 flop per FMA).
  * Used as the measured FP64 roofline denominator (MEASURED_PEAKS.json has no FP64 entry). */
 int ttvb_fp64_peak(ttvb_handle *h, double *tflops, float *ms);

@@ -29,7 +29,7 @@ MAX_PLANETS = 9
 
 EXPORTS = ["ttvb_last_error", "ttvb_version", "ttvb_device_count", "ttvb_create", "ttvb_destroy",
            "ttvb_set_cube_bounds", "ttvb_nsteps", "ttvb_loglike", "ttvb_ephemeris", "ttvb_cube_to_physical",
-           "ttvb_last_kernel_ms", "ttvb_launch_count", "ttvb_fp64_peak",
+           "ttvb_last_kernel_ms", "ttvb_launch_count", "ttvb_stream_retries", "ttvb_fp64_peak",
            "ttvb_pt_create", "ttvb_pt_destroy", "ttvb_pt_set_walkers", "ttvb_pt_run", "ttvb_pt_get", "ttvb_pt_half_begin", "ttvb_pt_half_end", "ttvb_pt_proposal_logl",
            "ttvb_selftest_philox", "ttvb_selftest_perm", "ttvb_selftest_seed_scan", "ttvb_check_failures"]
 
@@ -130,6 +130,7 @@ def lib():
     L.ttvb_cube_to_physical.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     L.ttvb_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     L.ttvb_launch_count.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+    L.ttvb_stream_retries.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
     L.ttvb_pt_create.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_double, C.c_double, C.c_double,
                                  C.c_uint64, C.c_int, C.POINTER(C.c_void_p)]
     L.ttvb_pt_destroy.argtypes = [C.c_void_p]

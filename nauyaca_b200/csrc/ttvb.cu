@@ -68,6 +68,9 @@ struct ttvb_handle {
     cudaStream_t s_in = nullptr, s_out = nullptr;
     int* h_ready = nullptr;          // pinned: row counts the copy-in stream writes to the device counter
     size_t h_ready_cap = 0;          // (one slot per upload piece of a call: a slot is read when its copy EXECUTES)
+    bool no_stream = false;          // TTVB_NO_STREAM=1: upload every launch before it starts
+    long long stream_retries = 0;    // streamed launches that had to be run again (uploads did not overlap)
+    bool test_stall = false;         // TTVB_STREAM_TEST_STALL=1 (tests): hold the uploads back until the kernel gives up
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_krn[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     bool timed = false;
     bool in_capture = false;     // the call is being captured into a CUDA graph: no events, no waits on outside work
@@ -267,6 +270,8 @@ int ttvb_create(const ttvb_system* sys, int device, ttvb_handle** out) {
     if (!h) return fail(TTVB_E_INVALID, "out of host memory");
     h->device = device;
     if (const char* e = std::getenv("TTVB_NSEG")) h->force_nseg = std::atoi(e);   // experiments / tests
+    if (const char* e = std::getenv("TTVB_NO_STREAM")) h->no_stream = std::atoi(e) != 0;
+    if (const char* e = std::getenv("TTVB_STREAM_TEST_STALL")) h->test_stall = std::atoi(e) != 0;
     h->npla = sys->npla; h->ndim = sys->ndim; h->nobs = sys->nobs;
     ttvb::DevSys& S = h->sys;
     S.npla = sys->npla; S.ndim = sys->ndim; S.nconst = sys->nconst; S.nobs = sys->nobs;
@@ -491,7 +496,7 @@ static int run_batch(ttvb_handle* h, const double* x, int64_t B, int mode, doubl
         // one pinned slot per upload piece of this call (at most ~log2(chunk/wave)+2 pieces per launch)
         size_t per_launch = 2;
         for (long long w = wave; w < chunk; w *= 2) per_launch++;
-        const size_t need = (size_t)nchunks * per_launch;
+        const size_t need = (size_t)nchunks * (per_launch + 1);          // + the launch's time-out flag
         if (need > h->h_ready_cap) {
             if (h->h_ready) CU(cudaFreeHost(h->h_ready));
             h->h_ready = nullptr; h->h_ready_cap = 0;
@@ -501,19 +506,69 @@ static int run_batch(ttvb_handle* h, const double* x, int64_t B, int mode, doubl
     }
     size_t slot = 0;
     CU(cudaEventRecord(h->ev0, st));
+    // what is left to do for a launch once its kernel is in the stream: look at its time-out flag
+    // (streamed launches), run it again if its uploads could not overlap, then download its results
+    struct Pending { bool valid = false, streamed = false; int bf = 0; long long b0 = 0, nb = 0; int* hflag = nullptr; ttvb::DevSys S; };
+    auto finish = [&](Pending& q) -> int {
+        if (!q.valid) return TTVB_OK;
+        unsigned char* d = h->d_stage + (size_t)q.bf * bytes;
+        if (q.streamed) {
+            CU(cudaEventSynchronize(h->ev_krn[q.bf]));
+            if (*q.hflag != 0) {
+                // the uploads did not run under the kernel (a tool serialising the GPU): its tiles gave up
+                // after a bounded wait; the rows have arrived by now, run the launch again without waiting
+                CU(cudaStreamSynchronize(h->s_in));
+                q.S.ready = nullptr;
+                int grid = 0;
+                int rc2 = plan_launch(h, q.S, st, &grid);
+                if (rc2 != TTVB_OK) return rc2;
+                rc2 = dispatch_launch(h, q.S, grid, st);
+                if (rc2 != TTVB_OK) return rc2;
+                CU(cudaEventRecord(h->ev_krn[q.bf], st));
+                h->stream_retries++;
+                h->no_stream = true;
+            }
+        }
+        cudaStream_t so = h->s_out;
+        const long long b0 = q.b0, nb = q.nb;
+        CU(cudaStreamWaitEvent(so, h->ev_krn[q.bf], 0));
+        if (chi2_out) CU(cudaMemcpyAsync(chi2_out + b0, d + off_chi2, (size_t)nb * 8, cudaMemcpyDeviceToHost, so));
+        if (logl_out) CU(cudaMemcpyAsync(logl_out + b0, d + off_logl, (size_t)nb * 8, cudaMemcpyDeviceToHost, so));
+        if (chi2_planet_out) CU(cudaMemcpyAsync(chi2_planet_out + b0 * N, d + off_pl, (size_t)nb * N * 8, cudaMemcpyDeviceToHost, so));
+        if (status_out) CU(cudaMemcpyAsync(status_out + b0, d + off_st, (size_t)nb * 4, cudaMemcpyDeviceToHost, so));
+        if (table) {
+            CU(cudaMemcpyAsync(n_events + b0, d + off_ne, (size_t)nb * 4, cudaMemcpyDeviceToHost, so));
+            CU(cudaMemcpyAsync(ev_planet + b0 * cap, d + off_ep, (size_t)nb * cap * 4, cudaMemcpyDeviceToHost, so));
+            CU(cudaMemcpyAsync(ev_epoch + b0 * cap, d + off_epo, (size_t)nb * cap * 4, cudaMemcpyDeviceToHost, so));
+            CU(cudaMemcpyAsync(ev_time + b0 * cap, d + off_et, (size_t)nb * cap * 8, cudaMemcpyDeviceToHost, so));
+            CU(cudaMemcpyAsync(ev_rsky + b0 * cap, d + off_er, (size_t)nb * cap * 8, cudaMemcpyDeviceToHost, so));
+            CU(cudaMemcpyAsync(ev_vsky + b0 * cap, d + off_ev, (size_t)nb * cap * 8, cudaMemcpyDeviceToHost, so));
+        }
+        CU(cudaEventRecord(h->ev_out[q.bf], so));
+        q.valid = false;
+        return TTVB_OK;
+    };
+    Pending prev;
     for (long long k = 0; k < nchunks; k++) {
         const int bf = (int)(k % nbuf);
         const long long b0 = k * chunk, nb = std::min<long long>(chunk, B - b0);
         unsigned char* d = h->d_stage + (size_t)bf * bytes;
         int* d_ready = (int*)(d + off_ready);
+        // Small launches (under two waves) are uploaded first and launched after: there is nothing to
+        // hide. A streamed kernel needs its uploads to run CONCURRENTLY with it, which tools that
+        // serialise the GPU (ncu, CUDA_LAUNCH_BLOCKING) do not allow: the first launch that finds this
+        // out (finish(): time-out flag, rerun) switches streaming off for the handle.
+        const bool streamed = nb >= 2 * wave && !h->no_stream;
         // ---- copy-in stream: the buffer is free once launch k-2 has been downloaded; zero the row
-        //      counter, then upload the rows piece by piece
+        //      counter (and the time-out flag next to it), then upload the rows piece by piece
         if (k >= nbuf) CU(cudaStreamWaitEvent(h->s_in, h->ev_out[bf], 0));
-        CU(cudaMemsetAsync(d_ready, 0, 4, h->s_in));
+        CU(cudaMemsetAsync(d_ready, 0, 8, h->s_in));
+        if (!streamed)
+            CU(cudaMemcpyAsync(d + off_x, x + b0 * rowlen, (size_t)nb * rowlen * 8, cudaMemcpyHostToDevice, h->s_in));
         CU(cudaEventRecord(h->ev_in[bf], h->s_in));
-        // ---- caller's stream: the kernel (its tiles wait for their rows)
+        // ---- caller's stream: the kernel (the tiles of a streamed launch wait for their rows)
         S.B = nb; S.x = (const double*)(d + off_x);
-        S.ready = d_ready;
+        S.ready = streamed ? d_ready : nullptr;
         S.chi2_out = chi2_out ? (double*)(d + off_chi2) : nullptr;
         S.logl_out = logl_out ? (double*)(d + off_logl) : nullptr;
         S.chi2_planet_out = chi2_planet_out ? (double*)(d + off_pl) : nullptr;
@@ -525,16 +580,20 @@ static int run_batch(ttvb_handle* h, const double* x, int64_t B, int mode, doubl
             S.n_events = nullptr; S.ev_planet = nullptr; S.ev_epoch = nullptr;
             S.ev_time = nullptr; S.ev_rsky = nullptr; S.ev_vsky = nullptr;
         }
-        CU(cudaStreamWaitEvent(st, h->ev_in[bf], 0));          // counter zeroed (and buffer free)
+        CU(cudaStreamWaitEvent(st, h->ev_in[bf], 0));          // counter zeroed / rows uploaded (and buffer free)
         int grid = 0;
         rc = plan_launch(h, S, st, &grid);
         if (rc != TTVB_OK) return rc;
         rc = dispatch_launch(h, S, grid, st);
         if (rc != TTVB_OK) return rc;
-        CU(cudaEventRecord(h->ev_krn[bf], st));
-        // ---- uploads (after the launch call, so that a pageable source, whose copies block the host,
-        //      cannot delay the launch)
-        {
+        Pending cur;
+        cur.valid = true; cur.streamed = streamed; cur.bf = bf; cur.b0 = b0; cur.nb = nb; cur.S = S;
+        // ---- uploads of a streamed launch (after the launch call, so that a pageable source, whose
+        //      copies block the host, cannot delay the launch)
+        if (streamed) {
+            if (h->test_stall) {                 // what a serialising profiler does: no upload while the kernel runs
+                cudaStreamSynchronize(st);
+            }
             long long done = 0, piece = std::min<long long>(wave, nb);
             while (done < nb) {
                 long long n = std::min<long long>(piece, nb - done);
@@ -548,24 +607,19 @@ static int run_batch(ttvb_handle* h, const double* x, int64_t B, int mode, doubl
                 CU(cudaMemcpyAsync(d_ready, hv, 4, cudaMemcpyHostToDevice, h->s_in));
                 piece *= 2;
             }
+            if (slot >= h->h_ready_cap) return fail(TTVB_E_INVALID, "internal: upload piece count");
+            cur.hflag = h->h_ready + slot++;
+            *cur.hflag = 0;
+            CU(cudaMemcpyAsync(cur.hflag, d_ready + 1, 4, cudaMemcpyDeviceToHost, st));    // after the kernel
         }
-        // ---- copy-out stream: results of this launch
-        cudaStream_t so = h->s_out;
-        CU(cudaStreamWaitEvent(so, h->ev_krn[bf], 0));
-        if (chi2_out) CU(cudaMemcpyAsync(chi2_out + b0, d + off_chi2, (size_t)nb * 8, cudaMemcpyDeviceToHost, so));
-        if (logl_out) CU(cudaMemcpyAsync(logl_out + b0, d + off_logl, (size_t)nb * 8, cudaMemcpyDeviceToHost, so));
-        if (chi2_planet_out) CU(cudaMemcpyAsync(chi2_planet_out + b0 * N, d + off_pl, (size_t)nb * N * 8, cudaMemcpyDeviceToHost, so));
-        if (status_out) CU(cudaMemcpyAsync(status_out + b0, d + off_st, (size_t)nb * 4, cudaMemcpyDeviceToHost, so));
-        if (table) {
-            CU(cudaMemcpyAsync(n_events + b0, d + off_ne, (size_t)nb * 4, cudaMemcpyDeviceToHost, so));
-            CU(cudaMemcpyAsync(ev_planet + b0 * cap, d + off_ep, (size_t)nb * cap * 4, cudaMemcpyDeviceToHost, so));
-            CU(cudaMemcpyAsync(ev_epoch + b0 * cap, d + off_epo, (size_t)nb * cap * 4, cudaMemcpyDeviceToHost, so));
-            CU(cudaMemcpyAsync(ev_time + b0 * cap, d + off_et, (size_t)nb * cap * 8, cudaMemcpyDeviceToHost, so));
-            CU(cudaMemcpyAsync(ev_rsky + b0 * cap, d + off_er, (size_t)nb * cap * 8, cudaMemcpyDeviceToHost, so));
-            CU(cudaMemcpyAsync(ev_vsky + b0 * cap, d + off_ev, (size_t)nb * cap * 8, cudaMemcpyDeviceToHost, so));
-        }
-        CU(cudaEventRecord(h->ev_out[bf], so));
+        CU(cudaEventRecord(h->ev_krn[bf], st));
+        // the previous launch is finished off only now, with this one already in the stream
+        rc = finish(prev);
+        if (rc != TTVB_OK) return rc;
+        prev = cur;
     }
+    rc = finish(prev);
+    if (rc != TTVB_OK) return rc;
     // the caller's stream ends after the last download; ev1 closes the timed region there
     for (int bf = 0; bf < nbuf; bf++) CU(cudaStreamWaitEvent(st, h->ev_out[bf], 0));
     CU(cudaEventRecord(h->ev1, st));
@@ -636,6 +690,12 @@ int ttvb_last_kernel_ms(ttvb_handle* h, float* ms) {
     CU(cudaSetDevice(h->device));
     CU(cudaEventSynchronize(h->ev1));
     CU(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+    return TTVB_OK;
+}
+
+int ttvb_stream_retries(const ttvb_handle* h, int64_t* count) {
+    if (!h || !count) return fail(TTVB_E_INVALID, "null argument");
+    *count = h->stream_retries;
     return TTVB_OK;
 }
 

@@ -653,15 +653,21 @@ ttvb_main_kernel(const __grid_constant__ DevSys S) {
             bool arrived = true;
             if (S.ready != nullptr) {
                 // streamed input: wait until the copy stream has delivered this tile's rows (rare: the
-                // uploads run ahead of the kernel). A bounded wait, so that a failed upload cannot hang
-                // the GPU: after ~2 s the tile gives up and reports TTVB_ST_INPUT_TIMEOUT.
+                // uploads run ahead of the kernel). A bounded wait (~0.3 s), so that uploads that cannot
+                // run under the kernel (a failed copy, a profiler serialising the GPU) cannot hang it:
+                // the tile gives up, flags it, and the host runs the launch again once the rows are there.
                 if (tid == 0) {
                     const int need = (int)(tile_base + nrow);
                     const long long t_start = clock64();
                     int ok = 1;
                     while (*reinterpret_cast<const volatile int*>(S.ready) < need) {
                         __nanosleep(1000);
-                        if (clock64() - t_start > 4000000000LL) { ok = 0; break; }
+                        // gave up before? then the rest of the launch gives up at once (the host reruns it)
+                        if (reinterpret_cast<const volatile int*>(S.ready)[1] != 0 || clock64() - t_start > 600000000LL) {
+                            ok = 0;
+                            atomicExch(const_cast<int*>(S.ready) + 1, 1);
+                            break;
+                        }
                     }
                     s_unit = ok ? unit : -1 - unit;
                 }

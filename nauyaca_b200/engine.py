@@ -210,6 +210,12 @@ class BatchEngine:
         _lib.check(_lib.lib().ttvb_launch_count(self._h, C.byref(n)))
         return int(n.value)
 
+    def stream_retries(self):
+        """Streamed host-pointer launches that had to be run again (see ttvb_stream_retries)."""
+        n = C.c_int64()
+        _lib.check(_lib.lib().ttvb_stream_retries(self._h, C.byref(n)))
+        return int(n.value)
+
     def fp64_peak_tflops(self):
         t = C.c_double(); ms = C.c_float()
         _lib.check(_lib.lib().ttvb_fp64_peak(self._h, C.byref(t), C.byref(ms)))

@@ -274,3 +274,34 @@ def test_two_engines_of_different_table_size_share_a_kernel(systems, oracle):
     raw.ephemeris(oracle.OracleSystem(spec).cube_to_physical(X[0])[None, :], mode=2)
     assert np.array_equal(big.loglike(X, mode=0)[0], ref)
     big.close()
+
+
+def test_streamed_host_path_and_its_fallback(systems, oracle):
+    """Host-pointer calls of two waves or more are streamed (tiles wait on the device for rows the copy
+    stream uploads meanwhile). Same bits as the resident path; and when the uploads cannot run under the
+    kernel (what a serialising profiler does; forced here with TTVB_STREAM_TEST_STALL) the launch gives up
+    after a bounded wait, is run again, and streaming is switched off for the handle."""
+    import json
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import json, sys, numpy as np
+sys.path.insert(0, %r)
+import torch, nauyaca_b200 as nb
+spec = json.load(open(%r))["doc2"]
+eng = nb.BatchEngine(spec)
+X = np.random.default_rng(5).random((90000, spec["ndim"]))         # 2.4 waves: streamed
+res = eng.loglike(torch.from_numpy(X).cuda(), mode=0); torch.cuda.synchronize()
+a = eng.loglike(X, mode=0); r1 = eng.stream_retries()
+b = eng.loglike(X, mode=0); r2 = eng.stream_retries()
+ok = all(np.array_equal(u, v.cpu().numpy()) for u, v in zip(a, res)) and all(np.array_equal(u, v) for u, v in zip(a, b))
+print(json.dumps({"ok": bool(ok), "retries": [r1, r2], "status_max": int(a[2].max())}))
+''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+       os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "systems.json"))
+    for stall, want in (("0", [0, 0]), ("1", [1, 1])):
+        out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, TTVB_STREAM_TEST_STALL=stall),
+                             capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-1500:]
+        rep = json.loads(out.stdout.strip().splitlines()[-1])
+        assert rep["ok"] and rep["retries"] == want and rep["status_max"] == 0, (stall, rep)
