@@ -62,6 +62,7 @@ struct ttvb_handle {
     unsigned char* d_ctx = nullptr;   // hand-over context of time-segmented runs
     size_t ctx_bytes = 0;
     int force_nseg = 0;          // TTVB_NSEG (0 = choose per launch)
+    int variant = 0;             // TTVB_VARIANT: 0 = choose per launch, 1 = unrolled refinement, 2 = compact refinement
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t ev_done = nullptr;   // end of the last launch that used the handle's scratch state
     // host-pointer calls: copy-in / copy-out streams and the events of the two staging buffers
@@ -89,12 +90,15 @@ int configure(ttvb_handle* h) {
     int optin = 0;
     CU(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
     cudaFuncAttributes fa;
-    CU(cudaFuncGetAttributes(&fa, ttvb::ttvb_main_kernel<N>));
+    CU(cudaFuncGetAttributes(&fa, ttvb::ttvb_main_kernel<N, false>));
     optin -= (int)fa.sharedSizeBytes;                 // the opt-in limit covers static + dynamic shared memory
     if (smem > (size_t)optin) return fail(TTVB_E_UNSUPPORTED, "observed table too large for shared memory (%zu B needed, %d B available)", smem, optin);
-    CU(cudaFuncSetAttribute(ttvb::ttvb_main_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
-    int nb = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ttvb::ttvb_main_kernel<N>, TTVB_TPB, smem));
+    CU(cudaFuncSetAttribute(ttvb::ttvb_main_kernel<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+    CU(cudaFuncSetAttribute(ttvb::ttvb_main_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+    int nb = 0, nb2 = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ttvb::ttvb_main_kernel<N, false>, TTVB_TPB, smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, ttvb::ttvb_main_kernel<N, true>, TTVB_TPB, smem));
+    nb = std::min(nb, nb2);
     if (nb < 1) return fail(TTVB_E_CUDA, "kernel does not fit on an SM (smem %zu B)", smem);
     h->blocks_per_sm = nb;
     h->tpb = TTVB_TPB;
@@ -154,7 +158,13 @@ int plan_launch(ttvb_handle* h, ttvb::DevSys& S, cudaStream_t st, int* grid_out)
 template <int N>
 int launch_main(ttvb_handle* h, const ttvb::DevSys& S, int grid, cudaStream_t st) {
     size_t smem = ttvb::smem_bytes(N, S.nobs, S.rowlen);
-    ttvb::ttvb_main_kernel<N><<<grid, TTVB_TPB, smem, st>>>(S);
+    // Two builds of the kernel that differ only in how compact the refinement code is (process_batch):
+    // a launch that fills the GPU with warps that refine often (more than ~1.5 events per warp-step
+    // over two waves or more: the 10^7 sweep) is instruction-cache bound and takes the compact one.
+    const bool dense = h->variant == 2 ||
+        (h->variant == 0 && S.B >= 2LL * h->max_grid * h->tpb && 32.0 * S.nobs >= 1.5 * (double)(S.nsteps + 1));
+    if (dense) ttvb::ttvb_main_kernel<N, true><<<grid, TTVB_TPB, smem, st>>>(S);
+    else ttvb::ttvb_main_kernel<N, false><<<grid, TTVB_TPB, smem, st>>>(S);
     CU(cudaGetLastError());
     h->launches++;
     return TTVB_OK;
@@ -271,6 +281,7 @@ int ttvb_create(const ttvb_system* sys, int device, ttvb_handle** out) {
     h->device = device;
     if (const char* e = std::getenv("TTVB_NSEG")) h->force_nseg = std::atoi(e);   // experiments / tests
     if (const char* e = std::getenv("TTVB_NO_STREAM")) h->no_stream = std::atoi(e) != 0;
+    if (const char* e = std::getenv("TTVB_VARIANT")) h->variant = std::atoi(e);
     if (const char* e = std::getenv("TTVB_STREAM_TEST_STALL")) h->test_stall = std::atoi(e) != 0;
     h->npla = sys->npla; h->ndim = sys->ndim; h->nobs = sys->nobs;
     ttvb::DevSys& S = h->sys;

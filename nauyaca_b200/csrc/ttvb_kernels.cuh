@@ -166,7 +166,7 @@ __host__ __device__ inline size_t smem_bytes(int N, int nobs, int rowlen) {
 // independent dependency chains per lane, which is what hides the FP64 latency here), and
 // hand the results to their owners. Per event the operation sequence is that of the scalar
 // form (kepler_drift / locate_bracket in ttvb_math.cuh), so the bits are the oracle's.
-template <int N>
+template <int N, bool COMPACT>
 __device__ __noinline__ void process_batch(const DevSys& S, int count, WarpQ Q, const double* kc_s,
                                            const double* q_s, const double* gm_s, int* res_i,
                                            double* res_d, int warp_base_tid, long long warp_base_sys,
@@ -200,13 +200,18 @@ __device__ __noinline__ void process_batch(const DevSys& S, int count, WarpQ Q, 
     double xs[2][2][3] = {}, vsn[2][2][3] = {}, gs[2][2];
     int which[2] = {1, 1};
     bool ok[2] = {true, true};
-#pragma unroll
+    // COMPACT: the two passes are a RUN-TIME loop (one copy of the drift code instead of two). The
+    // kernel is large and its warps are at different places of it; when the GPU is full of warps that
+    // refine often (the 10^7 sweep: 2.3 events per warp-step, `no_instruction` the second stall
+    // reason) the smaller footprint is worth 8 %; a sparse or latency-bound launch is ~1 % faster with
+    // the passes unrolled. The host picks the variant per launch (dispatch_launch).
+#pragma unroll (COMPACT ? 1 : 2)
     for (int pass = 0; pass < 2; pass++) {
-        double R[2][3], V[2][3];
+        double R[2][3], V[2][3], xt[2][3], vt[2][3];
 #pragma unroll
         for (int e = 0; e < 2; e++)
 #pragma unroll
-            for (int k = 0; k < 3; k++) { R[e][k] = 0.0; V[e][k] = 0.0; }
+            for (int k = 0; k < 3; k++) { R[e][k] = 0.0; V[e][k] = 0.0; xt[e][k] = 0.0; vt[e][k] = 0.0; }
 #pragma unroll 1
         for (int j = 0; j < N; j++) {
             const bool on0 = j <= planet[0], on1 = j <= planet[1];
@@ -232,8 +237,8 @@ __device__ __noinline__ void process_batch(const DevSys& S, int count, WarpQ Q, 
 #pragma unroll
                 for (int k = 0; k < 3; k++) {
                     const double xr = st.x[e][k] + R[e][k], vr = st.v[e][k] + V[e][k];
-                    xs[e][pass][k] = last ? xr : xs[e][pass][k];
-                    vsn[e][pass][k] = last ? vr : vsn[e][pass][k];
+                    xt[e][k] = last ? xr : xt[e][k];
+                    vt[e][k] = last ? vr : vt[e][k];
                     const double Rn = fma(qj, st.x[e][k], R[e][k]), Vn = fma(qj, st.v[e][k], V[e][k]);
                     R[e][k] = (j < planet[e]) ? Rn : R[e][k];
                     V[e][k] = (j < planet[e]) ? Vn : V[e][k];
@@ -242,8 +247,17 @@ __device__ __noinline__ void process_batch(const DevSys& S, int count, WarpQ Q, 
         }
 #pragma unroll
         for (int e = 0; e < 2; e++) {
-            gs[e][pass] = sky_g(xs[e][pass][0], xs[e][pass][1], vsn[e][pass][0], vsn[e][pass][1]);
-            if (pass == 0) which[e] = (gs[e][0] > 0.0) ? 0 : 2;
+            const double g = sky_g(xt[e][0], xt[e][1], vt[e][0], vt[e][1]);
+            if (pass == 0) {
+                gs[e][0] = g;
+                which[e] = (g > 0.0) ? 0 : 2;
+#pragma unroll
+                for (int k = 0; k < 3; k++) { xs[e][0][k] = xt[e][k]; vsn[e][0][k] = vt[e][k]; }
+            } else {
+                gs[e][1] = g;
+#pragma unroll
+                for (int k = 0; k < 3; k++) { xs[e][1][k] = xt[e][k]; vsn[e][1][k] = vt[e][k]; }
+            }
         }
     }
     // ---- the two sides of both brackets: behind sides together, then ahead sides together
@@ -529,7 +543,7 @@ __device__ __noinline__ bool run_steps(StepCtx<N>& cx, const double dt, const lo
     return full;
 }
 
-template <int N>
+template <int N, bool COMPACT>
 __global__ void __launch_bounds__(TTVB_TPB, TTVB_MINB)
 ttvb_main_kernel(const __grid_constant__ DevSys S) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -762,7 +776,7 @@ ttvb_main_kernel(const __grid_constant__ DevSys S) {
         cx.Time = Time; cx.Tm1 = Tm1; cx.Tm2 = Tm2;
         cx.qcount = 0; cx.k = k0; cx.pending_push = 0;
         while (run_steps<N>(cx, S.dt, S.nsteps, k1, o_cst, Q.qi, Q.qd)) {
-            process_batch<N>(S, TTVB_QCAP, Q, kc_s, q_s, gm_s, res_i, res_d, warp_base_tid, warp_base_sys, obs_epoch_s, obs_time_s, obs_sigma_s);
+            process_batch<N, COMPACT>(S, TTVB_QCAP, Q, kc_s, q_s, gm_s, res_i, res_d, warp_base_tid, warp_base_sys, obs_epoch_s, obs_time_s, obs_sigma_s);
             consume_results(lane, tid, res_i, res_d, acc_s, cur_s, cx.status);
             cx.qcount = 0;
         }
@@ -770,7 +784,7 @@ ttvb_main_kernel(const __grid_constant__ DevSys S) {
         {
             const int cnt = cx.qcount;   // warp-uniform
             if (cnt > 0) {
-                process_batch<N>(S, cnt, Q, kc_s, q_s, gm_s, res_i, res_d, warp_base_tid, warp_base_sys, obs_epoch_s, obs_time_s, obs_sigma_s);
+                process_batch<N, COMPACT>(S, cnt, Q, kc_s, q_s, gm_s, res_i, res_d, warp_base_tid, warp_base_sys, obs_epoch_s, obs_time_s, obs_sigma_s);
                 consume_results(lane, tid, res_i, res_d, acc_s, cur_s, cx.status);
             }
         }
