@@ -37,6 +37,9 @@ int fail(int code, const char* fmt, ...) {
     } while (0)
 
 constexpr long long CHUNK = 1LL << 20;   // systems per launch (bounds staging memory)
+#ifndef TTVB_COMPACT_MAX_N
+#define TTVB_COMPACT_MAX_N 3             // planet counts that also get the compact-refinement build of the kernel
+#endif
 
 }  // namespace
 
@@ -94,11 +97,14 @@ int configure(ttvb_handle* h) {
     optin -= (int)fa.sharedSizeBytes;                 // the opt-in limit covers static + dynamic shared memory
     if (smem > (size_t)optin) return fail(TTVB_E_UNSUPPORTED, "observed table too large for shared memory (%zu B needed, %d B available)", smem, optin);
     CU(cudaFuncSetAttribute(ttvb::ttvb_main_kernel<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
-    CU(cudaFuncSetAttribute(ttvb::ttvb_main_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
-    int nb = 0, nb2 = 0;
+    int nb = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ttvb::ttvb_main_kernel<N, false>, TTVB_TPB, smem));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, ttvb::ttvb_main_kernel<N, true>, TTVB_TPB, smem));
-    nb = std::min(nb, nb2);
+    if constexpr (N <= TTVB_COMPACT_MAX_N) {          // the compact build exists for the common planet counts
+        int nb2 = 0;
+        CU(cudaFuncSetAttribute(ttvb::ttvb_main_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, ttvb::ttvb_main_kernel<N, true>, TTVB_TPB, smem));
+        nb = std::min(nb, nb2);
+    }
     if (nb < 1) return fail(TTVB_E_CUDA, "kernel does not fit on an SM (smem %zu B)", smem);
     h->blocks_per_sm = nb;
     h->tpb = TTVB_TPB;
@@ -163,8 +169,13 @@ int launch_main(ttvb_handle* h, const ttvb::DevSys& S, int grid, cudaStream_t st
     // over two waves or more: the 10^7 sweep) is instruction-cache bound and takes the compact one.
     const bool dense = h->variant == 2 ||
         (h->variant == 0 && S.B >= 2LL * h->max_grid * h->tpb && 32.0 * S.nobs >= 1.5 * (double)(S.nsteps + 1));
-    if (dense) ttvb::ttvb_main_kernel<N, true><<<grid, TTVB_TPB, smem, st>>>(S);
-    else ttvb::ttvb_main_kernel<N, false><<<grid, TTVB_TPB, smem, st>>>(S);
+    if constexpr (N <= TTVB_COMPACT_MAX_N) {
+        if (dense) ttvb::ttvb_main_kernel<N, true><<<grid, TTVB_TPB, smem, st>>>(S);
+        else ttvb::ttvb_main_kernel<N, false><<<grid, TTVB_TPB, smem, st>>>(S);
+    } else {
+        (void)dense;
+        ttvb::ttvb_main_kernel<N, false><<<grid, TTVB_TPB, smem, st>>>(S);
+    }
     CU(cudaGetLastError());
     h->launches++;
     return TTVB_OK;
