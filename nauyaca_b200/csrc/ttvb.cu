@@ -65,6 +65,7 @@ struct ttvb_handle {
     unsigned char* d_ctx = nullptr;   // hand-over context of time-segmented runs
     size_t ctx_bytes = 0;
     int force_nseg = 0;          // TTVB_NSEG (0 = choose per launch)
+    int force_lanes = 0;         // TTVB_LANES (0 = choose per launch): systems on the first so many lanes of a warp
     int variant = 0;             // TTVB_VARIANT: 0 = choose per launch, 1 = unrolled refinement, 2 = compact refinement
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t ev_done = nullptr;   // end of the last launch that used the handle's scratch state
@@ -117,7 +118,24 @@ int configure(ttvb_handle* h) {
 // of T tiles on G resident CTAs takes ceil(T/G) rounds; with nseg segments it takes
 // ceil(nseg*T/G)/nseg). Sets S.nseg/seg_len/sched/ctx and returns the grid size.
 int plan_launch(ttvb_handle* h, ttvb::DevSys& S, cudaStream_t st, int* grid_out) {
-    const long long ntiles = (S.B + h->tpb - 1) / h->tpb;
+    // Thin launch: a batch of at most one warp per scheduler (num_sms * 4 warps) is latency-bound,
+    // and a good part of that latency is the event handling of a warp (a push phase on most steps,
+    // one refinement per 64 events), which grows with the number of systems the warp holds. Such a
+    // batch is spread over all the schedulers, only the first `lanes` lanes of every warp holding a
+    // system (a warp with few active lanes issues no faster, but it pushes and refines that many
+    // fewer events; two warps on a scheduler would each run ~1.4x longer, so one CTA per SM is the
+    // limit). Same bits: a system's arithmetic does not depend on its lane. TTVB_LANES forces it.
+    int lanes = 32;
+    if (S.ready == nullptr) {
+        if (h->force_lanes > 0) lanes = std::min(h->force_lanes, 32);
+        else {
+            const long long warps = (long long)h->num_sms * (h->tpb / 32);
+            lanes = (int)std::min<long long>(32, (S.B + warps - 1) / warps);
+        }
+    }
+    S.lanes = lanes;
+    const long long spt = (long long)(h->tpb / 32) * lanes;
+    const long long ntiles = (S.B + spt - 1) / spt;
     const long long G = h->max_grid;
     int best = 1;
     if (h->force_nseg > 0) {
@@ -292,6 +310,7 @@ int ttvb_create(const ttvb_system* sys, int device, ttvb_handle** out) {
     h->device = device;
     if (const char* e = std::getenv("TTVB_NSEG")) h->force_nseg = std::atoi(e);   // experiments / tests
     if (const char* e = std::getenv("TTVB_NO_STREAM")) h->no_stream = std::atoi(e) != 0;
+    if (const char* e = std::getenv("TTVB_LANES")) h->force_lanes = std::atoi(e);
     if (const char* e = std::getenv("TTVB_VARIANT")) h->variant = std::atoi(e);
     if (const char* e = std::getenv("TTVB_STREAM_TEST_STALL")) h->test_stall = std::atoi(e) != 0;
     h->npla = sys->npla; h->ndim = sys->ndim; h->nobs = sys->nobs;

@@ -92,6 +92,10 @@ struct DevSys {
     // streaming input (host-pointer calls): number of rows of `x` uploaded so far, bumped by the
     // copy stream while the kernel runs; a tile waits until its rows are there. nullptr: all there.
     const int* ready;
+    // thin launches (latency-bound batches that leave schedulers idle): only the first `lanes` lanes
+    // of a warp hold a system, so that the batch spreads over more warps and every warp pushes and
+    // refines fewer events (plan_launch chooses; 32 = every lane)
+    int lanes;
     double* ctx_d;            // [25N+3][ctx_stride]
     int* ctx_i;               // [2N+4][ctx_stride]
     long long ctx_stride;
@@ -589,7 +593,9 @@ ttvb_main_kernel(const __grid_constant__ DevSys S) {
         Q.qi = (int*)qb;
         Q.qd = (double*)(qb + TTVB_QCAP * 16);
     }
-    const long long ntiles = (S.B + TTVB_TPB - 1) / TTVB_TPB;
+    const int spt = (TTVB_TPB / 32) * S.lanes;        // systems per tile
+    const long long ntiles = (S.B + spt - 1) / spt;
+    const int slot_in_tile = warp * S.lanes + lane;   // of the systems this lane holds, if it holds one
     const int rowlen = S.rowlen;
 
     __shared__ int s_unit;
@@ -603,9 +609,10 @@ ttvb_main_kernel(const __grid_constant__ DevSys S) {
         const int seg = unit / (int)ntiles;
         const long long tile = unit - (long long)seg * ntiles;
         TTVB_CHECK(unit >= 0 && seg >= 0 && seg < S.nseg && tile >= 0 && tile < ntiles, CHK_UNIT);
-        const long long tile_base = tile * TTVB_TPB;
-        const long long sys = tile_base + tid;
-        bool alive = sys < S.B;
+        const long long tile_base = tile * spt;
+        const long long sys = tile_base + slot_in_tile;
+        const bool mine = lane < S.lanes && sys < S.B;   // this lane holds a system of the batch
+        bool alive = mine;
         int status = 0;
         SmemConsts<N> C{cst_s + tid};
         State<N> p = {};
@@ -629,7 +636,7 @@ ttvb_main_kernel(const __grid_constant__ DevSys S) {
             }
             __syncthreads();
             __threadfence();
-            if (sys < S.B) {
+            if (mine) {
                 const double* cd = S.ctx_d + sys;
                 const int* ci = S.ctx_i + sys;
                 const long long cs = S.ctx_stride;
@@ -663,7 +670,7 @@ ttvb_main_kernel(const __grid_constant__ DevSys S) {
         } else {
         // ---- first segment: coalesced staging of this tile's input rows, prologue
         {
-            const long long nrow = (S.B - tile_base < TTVB_TPB) ? (S.B - tile_base) : TTVB_TPB;
+            const long long nrow = (S.B - tile_base < spt) ? (S.B - tile_base) : spt;
             bool arrived = true;
             if (S.ready != nullptr) {
                 // streamed input: wait until the copy stream has delivered this tile's rows (rare: the
@@ -699,7 +706,7 @@ ttvb_main_kernel(const __grid_constant__ DevSys S) {
         __syncthreads();
         // ---- prologue: bounds, cube->physical, constants, elements -> Jacobi state
         if (alive) {
-            const double* xr = xstage + (size_t)tid * rowlen;
+            const double* xr = xstage + (size_t)slot_in_tile * rowlen;
             if (S.mode != 2) {
                 bool inside = true;
                 for (int i = 0; i < S.ndim; i++) {
@@ -710,7 +717,7 @@ ttvb_main_kernel(const __grid_constant__ DevSys S) {
             }
         }
         if (alive) {
-            const double* xr = xstage + (size_t)tid * rowlen;
+            const double* xr = xstage + (size_t)slot_in_tile * rowlen;
             double eta_prev = S.gm0;
             double R[3] = {0.0, 0.0, 0.0}, V[3] = {0.0, 0.0, 0.0};
             bool valid = true;
@@ -761,13 +768,13 @@ ttvb_main_kernel(const __grid_constant__ DevSys S) {
             if (!ok) { status |= 2; alive = false; }
         }
         }   // seg == 0
-        const bool integrate = (sys < S.B) && !(status & 1);   // out of bounds: chi2=+inf
+        const bool integrate = mine && !(status & 1);   // out of bounds: chi2=+inf
         // ---- integration of steps k0..k1 of this unit: the step loop is a leaf function with its
         //      own register allocation; it comes back whenever the warp's event queue is full
         const long long k0 = (long long)seg * S.seg_len + 1;
         const long long k1 = (seg == S.nseg - 1) ? (S.nsteps + 1) : (long long)(seg + 1) * S.seg_len;
         const int warp_base_tid = warp * 32;
-        const long long warp_base_sys = tile_base + warp_base_tid;
+        const long long warp_base_sys = tile_base + warp * S.lanes;
         StepCtx<N> cx;
         cx.p = p;
 #pragma unroll
@@ -795,7 +802,7 @@ ttvb_main_kernel(const __grid_constant__ DevSys S) {
         Time = cx.Time; Tm1 = cx.Tm1; Tm2 = cx.Tm2;
         if (seg < S.nseg - 1) {
             // ---- hand the tile over: save the context, publish the segment
-            if (sys < S.B) {
+            if (mine) {
                 double* cd = S.ctx_d + sys;
                 int* ci = S.ctx_i + sys;
                 const long long cs = S.ctx_stride;
@@ -829,7 +836,7 @@ ttvb_main_kernel(const __grid_constant__ DevSys S) {
             continue;
         }
         // ---- epilogue: remaining observed epochs are missing -> penalty; totals
-        if (sys < S.B) {
+        if (mine) {
             double chi2, logl;
             if (!integrate) {
                 chi2 = INFINITY; logl = -INFINITY;

@@ -213,6 +213,36 @@ def test_time_segmented_launch_is_bit_identical(oracle, systems, monkeypatch, ns
     eng.close()
 
 
+@pytest.mark.parametrize("lanes,nseg", [(1, 0), (5, 0), (9, 3), (16, 0), (27, 2), (32, 0), (0, 0)])
+def test_thin_launch_is_bit_identical(oracle, systems, monkeypatch, lanes, nseg):
+    """A thin launch (systems on the first `lanes` lanes of every warp only: what plan_launch picks for
+    batches of at most one warp per scheduler; 0 = its own choice) gives the bits of the full-warp launch
+    and of the oracle - chi2, status, per-planet values and the event table, also when cut into time
+    segments, with an out-of-bounds row and a ragged last tile."""
+    import nauyaca_b200 as nb
+    spec = systems["sys3"]; osys = oracle.OracleSystem(spec)
+    X = np.random.default_rng(32).random((701, spec["ndim"]))
+    X[5, 0] = 2.0
+    if lanes:
+        monkeypatch.setenv("TTVB_LANES", str(lanes))
+    if nseg:
+        monkeypatch.setenv("TTVB_NSEG", str(nseg))
+    eng = nb.BatchEngine(spec)
+    chi2, logl, st, per = eng.loglike(X, mode=0, per_planet=True)
+    o = osys.loglike(X, mode=0)
+    _same(st, o[2]); _same(chi2, o[0]); _same(logl, o[1])
+    import torch
+    r = eng.loglike(torch.from_numpy(X[:333]).cuda(), mode=0)            # device pointers, another batch size
+    _same(r[0].cpu().numpy(), o[0][:333])
+    flat, _ = eng.cube_to_physical(X[:41])
+    n, pl, ep, tm, rs, vs, st2 = eng.ephemeris(flat, mode=2, cap=200)
+    for b in range(41):
+        e = oracle.ephemeris(flat[b], spec["mstar"], spec["t0"], spec["dt"], spec["ftime"], cap=200)
+        assert n[b] == len(e[3])
+        _same(tm[b, :n[b]], e[3]); _same(ep[b, :n[b]], e[2]); _same(pl[b, :n[b]], e[1])
+    eng.close()
+
+
 def test_observed_table_variants(oracle):
     """Planets without observations, unsorted epoch order in the table, epochs the simulation
     never reaches (1e20 each, utils.py:199-206), barycentric-Julian-date sized times."""
