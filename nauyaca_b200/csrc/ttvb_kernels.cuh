@@ -128,6 +128,20 @@ struct SmemConsts {
     }
 };
 
+// The same constants for one pass through the step loop, with the one the kick needs first (q_0, the
+// first operand of its first multiplication) already in a register: its shared-memory load is issued
+// ahead of the history-ring stores instead of right in front of its use.
+template <int N>
+struct StepConsts {
+    const SmemConsts<N>& c;
+    double q0;
+    __device__ __forceinline__ double gm(int i) const { return c.gm(i); }
+    __device__ __forceinline__ double kc(int i) const { return c.kc(i); }
+    __device__ __forceinline__ double q(int i) const { return i == 0 ? q0 : c.q(i); }
+    __device__ __forceinline__ double ieta(int i) const { return c.ieta(i); }
+    __device__ __forceinline__ double s(int i) const { return c.s(i); }
+};
+
 // Stores into the warp's event queue carry an L2 evict-last policy: the queues are rewritten
 // every few dozen steps and should stay resident in L2 instead of being written back to HBM.
 __device__ __forceinline__ unsigned long long q_policy() {
@@ -416,42 +430,53 @@ __device__ __noinline__ bool run_steps(StepCtx<N>& cx, const double dt, const lo
     long long k = cx.k;
     bool full = false;
     constexpr int CPR = (12 * N + 31) / 32;
-    // ONE warp reduction per step tells both what the push phase and the loop head need to know:
-    // bits 0..N-1 = planets that triggered in some lane, bit 31 = some lane still has a live system.
-    // It is issued right after the trigger check of a step and consumed after the arithmetic of the
-    // next one, so its latency is hidden (a superset of the planets is harmless: the per-planet
-    // ballot of the push phase then comes back empty).
-    unsigned warp_state = __reduce_or_sync(0xffffffffu, (unsigned)trigmask | (alive ? 0x80000000u : 0u));
+    // Two warp votes per step tell what the push phase and the loop head need to know: whether some
+    // lane holds an untold event, and whether some lane still has a live system. They are taken at the top of
+    // a step, on what the trigger check of the step before has left, and consumed after the arithmetic
+    // of the step (votes, not a REDUX reduction: its result comes back through a uniform register that
+    // the compiler copies to a vector register at once, and an in-order warp then waits for it).
+    unsigned ev_lanes = __ballot_sync(0xffffffffu, trigmask != 0);
+    bool warp_alive = __any_sync(0xffffffffu, alive) != 0;
+    // The loop head looks at the vote of the step BEFORE the last (a warp whose systems have all
+    // stopped takes one more step on dead registers and leaves then).
+    bool some_alive = warp_alive;
+    // the step counters as 32-bit distances (at most 2e9 steps, ttvb_create): steps left in this call
+    // and steps left in the integration, so that the tests of the loop read no 64-bit parameter
+    int togo = (int)(k1 - k), left = (int)(nsteps - k);
+    // (ptxas lays the blocks of the loop out in program order whatever the source says - the rare
+    // Kepler iterations and the push phase moved behind the return with gotos came back in line - so
+    // the common path jumps over both; a lone warp pays a fetch redirect for each.)
     // a call that comes back from a refinement in the middle of a push phase re-enters there
     if (pending) { pending = false; goto push_phase; }
 #pragma unroll 1
     for (;;) {
+        if (togo < 0) break;
+        if (!some_alive) break;
+        ev_lanes = __ballot_sync(0xffffffffu, trigmask != 0);
+        warp_alive = __any_sync(0xffffffffu, alive) != 0;
+        // every lane steps; one without a live system computes on whatever its registers
+        // hold, on the straight-line path (idle flag), and nothing of it is ever used
         {
-            if (k > k1) break;
-            if (!(warp_state & 0x80000000u)) break;
-            {
-                // every lane steps; one without a live system computes on whatever its registers
-                // hold, on the straight-line path (idle flag), and nothing of it is ever used
-                double* hs = hist + (size_t)((k - 1) & 1) * 6 * N * TTVB_RS + tid;
+            const StepConsts<N> Cs{C, C.q(0)};
+            double* hs = hist + (size_t)((k - 1) & 1) * 6 * N * TTVB_RS + tid;
 #pragma unroll
-                for (int i = 0; i < N; i++)
+            for (int i = 0; i < N; i++)
 #pragma unroll
-                    for (int c = 0; c < 3; c++) {
-                        hs[(i * 6 + c) * TTVB_RS] = p.x[i][c];
-                        hs[(i * 6 + 3 + c) * TTVB_RS] = p.v[i][c];
-                    }
-                double rj[N], irj[N];
-                map_B<N>(C, p, dt, rj, irj);
-                if (!map_A_after_B<N>(C, p, dt, rj, irj, !alive)) { status |= 2; alive = false; trigmask = 0; }
-            }
-            Tm2 = Tm1; Tm1 = Time; Time += dt;
+                for (int c = 0; c < 3; c++) {
+                    hs[(i * 6 + c) * TTVB_RS] = p.x[i][c];
+                    hs[(i * 6 + 3 + c) * TTVB_RS] = p.v[i][c];
+                }
+            double rj[N], irj[N];
+            map_B<N>(Cs, p, dt, rj, irj);
+            if (!map_A_after_B<N>(Cs, p, dt, rj, irj, !alive)) { status |= 2; alive = false; trigmask = 0; }
         }
+        Tm2 = Tm1; Tm1 = Time; Time += dt;
     push_phase:
         // ---- push the events triggered at step k-1 (they now have p_{k-2}, p_{k-1}, p_k). The two
         //      older states are in the ring: all 32 lanes copy them together, one field each; the
         //      owner adds p_k from its registers and the header.
-        unsigned pm = warp_state & 0x7fffffffu;                               // planets that triggered somewhere in the warp
-        if (pm != 0u) {
+        some_alive = warp_alive;
+        if (ev_lanes != 0u) {
             __syncwarp();
             const unsigned long long pol = q_policy();
             const int par_old = (int)(k & 1) * 6 * N * TTVB_RS;     // ring slot of p_{k-2}; the other holds p_{k-1}
@@ -464,7 +489,7 @@ __device__ __noinline__ bool run_steps(StepCtx<N>& cx, const double dt, const lo
             {
                 unsigned tx;
                 asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tx));
-#pragma unroll
+    #pragma unroll
                 for (int r = 0; r < CPR; r++) {
                     const int e = (int)(tx & 31u) + 32 * r;
                     cp_ok[r] = e < 12 * N;
@@ -479,6 +504,8 @@ __device__ __noinline__ bool run_steps(StepCtx<N>& cx, const double dt, const lo
             // lane are copied by the whole warp, then all owners store their part side by side. A
             // lane tells its events in ascending planet order, so the per-system order of the
             // events (and of the chi2 sum) is the reference's.
+            // (a fresh ballot: a lane whose system has just stopped drops its pending events, so the
+            // vote taken at the top of the step may name lanes that have nothing to tell any more)
             unsigned evl = __ballot_sync(0xffffffffu, trigmask != 0);
             while (evl != 0u) {
                 const int room = TTVB_QCAP - qcount;
@@ -493,7 +520,7 @@ __device__ __noinline__ bool run_steps(StepCtx<N>& cx, const double dt, const lo
                         TTVB_CHECK(qcount + taken >= 0 && qcount + taken < TTVB_QCAP && b >= 0 && b < 32, CHK_QUEUE_SLOT);
                         double* dst = qdq + (qcount + taken) * QLayout<N>::SD;
                         taken++;
-#pragma unroll
+    #pragma unroll
                         for (int r = 0; r < CPR; r++)
                             if (cp_ok[r]) q_st(dst + cp_dst[r], src[cp_src[r]], pol);
                     }
@@ -503,12 +530,12 @@ __device__ __noinline__ bool run_steps(StepCtx<N>& cx, const double dt, const lo
                     const int slot = qcount + rank;
                     TTVB_CHECK(slot >= 0 && slot < TTVB_QCAP && i < N, CHK_QUEUE_SLOT);
                     int ci = 0;
-#pragma unroll
+    #pragma unroll
                     for (int j = 0; j < N; j++) if (j == i) { ci = count[j]; count[j] = ci + 1; }
                     q_st4(qi + 4 * slot, lane, i, ci, nev, pol);
                     nev++;
                     double* qd = qdq + slot * QLayout<N>::SD + 2 * 6 * N;
-#pragma unroll
+    #pragma unroll
                     for (int j = 0; j < N; j++) {
                         q_st2(qd + j * 6 + 0, p.x[j][0], p.x[j][1], pol);
                         q_st2(qd + j * 6 + 2, p.x[j][2], p.v[j][0], pol);
@@ -527,7 +554,7 @@ __device__ __noinline__ bool run_steps(StepCtx<N>& cx, const double dt, const lo
             if (full) { pending = true; break; }   // come back to the push phase of this step
         }
         // ---- trigger check of step k (unsynchronised Jacobi state, as TTVFast)
-        if (alive && k <= nsteps) {
+        if (alive && left >= 0) {
 #pragma unroll
             for (int i = 0; i < N; i++) {
                 const double cd = sky_g(p.x[i][0], p.x[i][1], p.v[i][0], p.v[i][1]);
@@ -535,8 +562,7 @@ __device__ __noinline__ bool run_steps(StepCtx<N>& cx, const double dt, const lo
                 prev_dot[i] = cd;
             }
         }
-        warp_state = __reduce_or_sync(0xffffffffu, (unsigned)trigmask | (alive ? 0x80000000u : 0u));
-        k++;
+        k++; togo--; left--;
     }
     cx.p = p;
 #pragma unroll
