@@ -128,12 +128,27 @@ struct SmemConsts {
     }
 };
 
+// The dynamic shared memory as an array of doubles (every `extern __shared__` array starts at the same
+// address). The step loop indexes THIS array with integers: a pointer derived from it is a generic
+// pointer to the compiler, which rebuilt its shared-window base (S2R SR_CgaCtaId + LEA, ~35 exposed
+// cycles for a lone warp) on every pass of the loop.
+extern __shared__ __align__(16) double ttvb_smem_d[];
+template <int N>
+struct SmemConstsIdx {
+    int off;     // o_cst + tid
+    __device__ __forceinline__ double gm(int i) const { return ttvb_smem_d[off + (0 * N + i) * TTVB_TPB]; }
+    __device__ __forceinline__ double kc(int i) const { return ttvb_smem_d[off + (1 * N + i) * TTVB_TPB]; }
+    __device__ __forceinline__ double q(int i) const { return ttvb_smem_d[off + (2 * N + i) * TTVB_TPB]; }
+    __device__ __forceinline__ double ieta(int i) const { return ttvb_smem_d[off + (3 * N + i) * TTVB_TPB]; }
+    __device__ __forceinline__ double s(int i) const { return ttvb_smem_d[off + (4 * N + i) * TTVB_TPB]; }
+};
+
 // The same constants for one pass through the step loop, with the one the kick needs first (q_0, the
 // first operand of its first multiplication) already in a register: its shared-memory load is issued
 // ahead of the history-ring stores instead of right in front of its use.
 template <int N>
 struct StepConsts {
-    const SmemConsts<N>& c;
+    const SmemConstsIdx<N>& c;
     double q0;
     __device__ __forceinline__ double gm(int i) const { return c.gm(i); }
     __device__ __forceinline__ double kc(int i) const { return c.kc(i); }
@@ -413,11 +428,9 @@ struct StepCtx {
 template <int N>
 __device__ __noinline__ bool run_steps(StepCtx<N>& cx, const double dt, const long long nsteps, const long long k1,
                                        const int o_cst, int* __restrict__ qi, double* __restrict__ qdq) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* const sd = reinterpret_cast<double*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31;
-    double* const hist = sd;
-    SmemConsts<N> C{sd + o_cst + tid};
+    double* const hist = ttvb_smem_d;            // the history ring starts the dynamic shared memory
+    const SmemConstsIdx<N> C{o_cst + tid};
     State<N> p = cx.p;
     double prev_dot[N];
     int count[N];
@@ -458,13 +471,13 @@ __device__ __noinline__ bool run_steps(StepCtx<N>& cx, const double dt, const lo
         // hold, on the straight-line path (idle flag), and nothing of it is ever used
         {
             const StepConsts<N> Cs{C, C.q(0)};
-            double* hs = hist + (size_t)((k - 1) & 1) * 6 * N * TTVB_RS + tid;
+            const int hs = (int)((k - 1) & 1) * 6 * N * TTVB_RS + tid;
 #pragma unroll
             for (int i = 0; i < N; i++)
 #pragma unroll
                 for (int c = 0; c < 3; c++) {
-                    hs[(i * 6 + c) * TTVB_RS] = p.x[i][c];
-                    hs[(i * 6 + 3 + c) * TTVB_RS] = p.v[i][c];
+                    hist[hs + (i * 6 + c) * TTVB_RS] = p.x[i][c];
+                    hist[hs + (i * 6 + 3 + c) * TTVB_RS] = p.v[i][c];
                 }
             double rj[N], irj[N];
             map_B<N>(Cs, p, dt, rj, irj);
@@ -516,13 +529,13 @@ __device__ __noinline__ bool run_steps(StepCtx<N>& cx, const double dt, const lo
                     while (mm != 0u && taken < room) {
                         const int b = __ffs(mm) - 1;
                         mm &= mm - 1u;
-                        const double* src = hist + (tid - lane + b);
+                        const int src = tid - lane + b;
                         TTVB_CHECK(qcount + taken >= 0 && qcount + taken < TTVB_QCAP && b >= 0 && b < 32, CHK_QUEUE_SLOT);
                         double* dst = qdq + (qcount + taken) * QLayout<N>::SD;
                         taken++;
     #pragma unroll
                         for (int r = 0; r < CPR; r++)
-                            if (cp_ok[r]) q_st(dst + cp_dst[r], src[cp_src[r]], pol);
+                            if (cp_ok[r]) q_st(dst + cp_dst[r], hist[src + cp_src[r]], pol);
                     }
                 }
                 if (trigmask != 0 && rank < room) {
@@ -554,11 +567,14 @@ __device__ __noinline__ bool run_steps(StepCtx<N>& cx, const double dt, const lo
             if (full) { pending = true; break; }   // come back to the push phase of this step
         }
         // ---- trigger check of step k (unsynchronised Jacobi state, as TTVFast)
-        if (alive && left >= 0) {
+        //      (straight-line: what a stopped system or the extra last step leaves in prev_dot is never read)
+        {
+            const bool chk = alive && left >= 0;
 #pragma unroll
             for (int i = 0; i < N; i++) {
                 const double cd = sky_g(p.x[i][0], p.x[i][1], p.v[i][0], p.v[i][1]);
-                if (prev_dot[i] < 0.0 && cd > 0.0 && p.x[i][2] > 0.0) trigmask |= (1 << i);
+                const bool trig = chk && prev_dot[i] < 0.0 && cd > 0.0 && p.x[i][2] > 0.0;
+                trigmask |= trig ? (1 << i) : 0;
                 prev_dot[i] = cd;
             }
         }
