@@ -265,15 +265,52 @@ class _OracleEngineShim:
 
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler:
+    """SM clock, power and throttle reasons of one GPU DURING the timed region: an NVML polling thread
+    (a sample every 10 ms, the first one at once - `nvidia-smi -lms` needs ~0.5 s to come up on an
+    8-GPU box and then misses a short region), nvidia-smi as the fall-back where NVML does not load."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, gpu_index):
         self.idx = gpu_index
         self.proc = None
+        self.thread = None
+        self.samples = []          # (sm_mhz, max_mhz, watts, reason bits)
+
+    def _nvml_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if self.idx < len(ids) and ids[self.idx].isdigit():
+                return int(ids[self.idx])
+        return self.idx
 
     def start(self):
+        try:
+            import threading
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self._nvml_index())
+            mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self._stop = threading.Event()
+
+            def poll():
+                while True:
+                    try:
+                        self.samples.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), mx,
+                                             nv.nvmlDeviceGetPowerUsage(h) / 1000.0,
+                                             int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))))
+                    except Exception:
+                        pass
+                    if self._stop.wait(0.01):
+                        return
+            self.thread = threading.Thread(target=poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
@@ -282,6 +319,17 @@ class ClockSampler:
             self.proc = None
 
     def stop(self):
+        if self.thread is not None:
+            self._stop.set()
+            self.thread.join(timeout=2)
+            if not self.samples:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+            bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+            # the samples under load: the region starts and may end at the idle clock
+            sm = [x[0] for x in self.samples]
+            reasons = sorted(n for n, b in bits.items() if any(x[3] & b for x in self.samples))
+            return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                    "power_w_max": float(max(x[2] for x in self.samples)), "samples": len(sm), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -291,7 +339,6 @@ class ClockSampler:
             self.proc.kill()
             out = ""
         sm, mx, reasons, pw = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in out.strip().splitlines():
             f = [x.strip() for x in line.split(",")]
             if len(f) < 8:
@@ -300,13 +347,13 @@ class ClockSampler:
                 sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
             except ValueError:
                 continue
-            for nme, v in zip(names, f[4:8]):
+            for nme, v in zip(self.NAMES, f[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(nme)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "power_w_max": float(max(pw)), "samples": len(sm)}
+                "power_w_max": float(max(pw)), "samples": len(sm), "source": "nvidia-smi"}
 
 
 # ----------------------------------------------------------------------------- GPU side

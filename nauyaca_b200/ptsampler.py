@@ -414,12 +414,14 @@ class DeviceSampler:
                 seed = int(box[0])
         elif self._world > 1:
             self._same_on_all_ranks(int(seed), "seed")
-        if self._world > 1 and self.ntemps * (self.nwalkers // 2) < 37888:
+        if self._world > 1 and self.ntemps * (self.nwalkers // 2) < 18944:
             import warnings
-            warnings.warn(f"sharded DeviceSampler: a half-step of {self.ntemps * (self.nwalkers // 2)} proposals is one "
-                          "warp-latency long on ANY number of GPUs (a B200 holds 37 888 systems per wave); sharding it "
-                          "does not shorten the iteration (measured: 2.81 ms on 1 GPU, 2.87 ms sharded over 8, "
-                          "profiles/r2s_bench_c3*). Use one replica of the ensemble per GPU instead.", stacklevel=2)
+            warnings.warn(f"sharded DeviceSampler: a half-step of {self.ntemps * (self.nwalkers // 2)} proposals is "
+                          "latency-bound on ANY number of GPUs (below one warp per scheduler, 18 944 systems on a B200, "
+                          "a launch takes about one warp-latency): sharding it shortens the iteration only through the "
+                          "fewer events every warp then handles (measured, 10 x 1000 walkers: 1.92 ms on 1 GPU, 1.85 ms "
+                          "sharded over 2, 1.79 ms over 8, profiles/r2x_bench_c3*). For throughput run one replica of "
+                          "the ensemble per GPU instead.", stacklevel=2)
         self._pt = C.c_void_p()
         _lib.check(_lib.lib().ttvb_pt_create(engine._h, self.ntemps, self.nwalkers, self._betas.ctypes.data, float(a),
                                              float(adaptation_lag), float(adaptation_time), C.c_uint64(seed),
