@@ -132,21 +132,23 @@ def calculate_ephemeris(PSystem, flat_params):
 
 
 def _chi2(observed, sigma, simulated, individual=False):
-    """utils.py:161-216 (host dictionaries; the GPU computes the same sum in-kernel)."""
-    ind_chi2 = {}
-    chi2_tot = 0.0
-    for planet_id, obs in observed.items():
-        chi2 = 0.0
-        sim = simulated[planet_id]
-        sig = sigma[planet_id]
-        for epoch, times_obs in obs.items():
-            if epoch in sim:
-                chi2 += ((times_obs - sim[epoch]) / sig[epoch]) ** 2
-            else:
-                chi2 += 1e+20
-        chi2_tot += chi2
-        ind_chi2[planet_id] = chi2
-    return ind_chi2 if individual else chi2_tot
+    """utils.py:161-216 on host dictionaries (the GPU computes the same sum in-kernel): per planet, in
+    the order of its observed epochs, ((t_obs - t_sim) / sigma)^2, and 1e20 for an observed epoch the
+    simulation does not have; the planets' sums are added in dictionary order."""
+    per_planet = {}
+    for pid, table in observed.items():
+        model, err = simulated[pid], sigma[pid]
+        acc = 0.0
+        for ep, t_obs in table.items():
+            t_sim = model.get(ep)
+            acc += 1e+20 if t_sim is None else ((t_obs - t_sim) / err[ep]) ** 2
+        per_planet[pid] = acc
+    if individual:
+        return per_planet
+    total = 0.0
+    for v in per_planet.values():
+        total += v
+    return total
 
 
 def intervals(frontiers, flat_params):
