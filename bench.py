@@ -497,6 +497,10 @@ def run_gpu(args):
                          "traffic_source": traffic["source"] if traffic else None,
                          "traffic_note": "above the algorithmic bytes by the context hand-over of time-segmented scheduling (DESIGN.md)",
                          "peak_source": "FP64 FMA-chain microbenchmark in this run (MEASURED_PEAKS.json has no FP64 entry)",
+                         "peak_note": "the peak chains fma(c, const, const); with register operands taken from other in-flight "
+                                      "chains, as the step loop's DFMAs have them, the same pipe sustains 66-77 % of nominal "
+                                      "(profiles/r2y_fp64_register_operands.txt); ncu: pipe 73 % active over a C4 launch "
+                                      "(profiles/r2z_c4_full.txt)",
                          "nominal_peak": nominal, "frac_of_nominal": achieved / nominal,
                          "kernel_ms": kms, "flop_per_eval": f_eval,
                          "hbm": {"algorithmic_bytes_per_launch": int(B * (ndim + 2) * 8 + B * 4),
