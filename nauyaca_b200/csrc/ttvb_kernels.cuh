@@ -796,6 +796,10 @@ ttvb_main_kernel(const __grid_constant__ DevSys S) {
             }
             if (!valid) { status |= 16; alive = false; }
         }
+        // The input staging area ALIASES the history ring: no warp may start stepping (and store into
+        // the ring) before every warp of the CTA has read its rows. Only timing kept them apart before:
+        // a warp would have had to fall ~10^4 cycles behind in its prologue, which nothing rules out.
+        __syncthreads();
 #pragma unroll
         for (int i = 0; i < N; i++) {
             prev_dot[i] = 0.0; count[i] = 0;

@@ -6,7 +6,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import nauyaca_b200 as nb
 spec = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "systems.json")))["doc2"]
 eng = nb.BatchEngine(spec)
-for B in (10000, 37888, 75776, 400000):
+for B in (32, 592, 2368, 5000, 10000, 18944, 37888, 75776, 400000):
     X = np.random.default_rng(1).random((B, spec["ndim"]))
     Xd = torch.from_numpy(X).cuda()
     ms = []
