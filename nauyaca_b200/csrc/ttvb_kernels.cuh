@@ -675,6 +675,7 @@ ttvb_main_kernel(const __grid_constant__ DevSys S) {
 #else
                 while (*flag < seg) __nanosleep(256);
 #endif
+                __threadfence();     // acquire: the observation of the flag, then a fence, in the observing thread
             }
             __syncthreads();
             __threadfence();
@@ -733,6 +734,7 @@ ttvb_main_kernel(const __grid_constant__ DevSys S) {
                         }
                     }
                     s_unit = ok ? unit : -1 - unit;
+                    __threadfence();     // acquire (the row counter was observed by this thread)
                 }
                 __syncthreads();
                 __threadfence();
