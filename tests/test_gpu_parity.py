@@ -261,3 +261,27 @@ def test_g5_long_baseline_on_gpu(oracle, systems, dt, key):
     assert np.array_equal(tm[0, :k], o[3]) and np.array_equal(ep[0, :k], o[2]) and np.array_equal(rs[0, :k], o[4])
     assert np.all(rs[0, :k] <= spec["rstarAU"])
     eng.close()
+
+
+def test_two_body_closed_form_on_gpu():
+    """The known answers of tests/test_oracle_properties.py through the C ABI (ttvb_ephemeris, N = 1 and
+    N = 2 kernels): two-body transit times against the closed form, no golden and no oracle involved."""
+    import nauyaca_b200 as nb
+    from test_oracle_properties import CASES, _analytic_transits
+    mstar, t0, dt, tend = 0.8, 2.5, 0.05, 120.0
+    for mass, P, e, w, M0, Om in CASES:
+        SP = nb.utils.run_TTVFast([mass, P, e, 90.0, w, M0, Om], mstar, init_time=t0, final_time=tend, dt=dt)
+        tm = SP[2]
+        want = _analytic_transits(P, e, w, M0, t0, tend)
+        want = want[(want > t0 + dt) & (want < tend - dt)]
+        got = tm[(tm > t0 + dt) & (tm < tend - dt)]
+        assert len(got) == len(want) and np.max(np.abs(got - want)) < 2e-10
+    # massless pair: two independent orbits
+    flat = [1e-7, 5.3, 0.1, 90.0, 40.0, 100.0, 0.0, 1e-7, 8.9, 0.2, 90.0, 250.0, 30.0, 0.0]
+    SP = nb.utils.run_TTVFast(flat, 1.1, init_time=0.0, final_time=150.0, dt=0.04)
+    for j, (P, e, w, M0) in enumerate([(5.3, 0.1, 40.0, 100.0), (8.9, 0.2, 250.0, 30.0)]):
+        t = SP[2][SP[0] == j]
+        want = _analytic_transits(P, e, w, M0, 0.0, 150.0)
+        want = want[(want > 0.04) & (want < 150.0 - 0.04)]
+        t = t[(t > 0.04) & (t < 150.0 - 0.04)]
+        assert len(t) == len(want) and np.max(np.abs(t - want)) < 5e-9
