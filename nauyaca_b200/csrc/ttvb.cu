@@ -118,7 +118,7 @@ int configure(ttvb_handle* h) {
 // of T tiles on G resident CTAs takes ceil(T/G) rounds; with nseg segments it takes
 // ceil(nseg*T/G)/nseg). Sets S.nseg/seg_len/sched/ctx and returns the grid size.
 int plan_launch(ttvb_handle* h, ttvb::DevSys& S, cudaStream_t st, int* grid_out) {
-    // Thin launch: a batch of at most one warp per scheduler (num_sms * 4 warps) is latency-bound,
+    // Thin launch: a batch that fits the resident grid (at most blocks_per_sm warps per scheduler) is latency-bound,
     // and a good part of that latency is the event handling of a warp (a push phase on most steps,
     // one refinement per 64 events), which grows with the number of systems the warp holds. Such a
     // batch is spread over all the schedulers, only the first `lanes` lanes of every warp holding a
@@ -129,8 +129,12 @@ int plan_launch(ttvb_handle* h, ttvb::DevSys& S, cudaStream_t st, int* grid_out)
     if (S.ready == nullptr) {
         if (h->force_lanes > 0) lanes = std::min(h->force_lanes, 32);
         else {
+            // k resident CTAs per SM are needed at 32 lanes per warp; while the batch fits the resident
+            // grid (k <= blocks_per_sm) it is spread evenly over k CTAs on EVERY SM (one more CTA on
+            // a few SMs only would make those, and so the launch, as slow as a full second wave)
             const long long warps = (long long)h->num_sms * (h->tpb / 32);
-            lanes = (int)std::min<long long>(32, (S.B + warps - 1) / warps);
+            const long long k = (S.B + warps * 32 - 1) / (warps * 32);
+            if (k <= h->blocks_per_sm) lanes = (int)std::min<long long>(32, (S.B + warps * k - 1) / (warps * k));
         }
     }
     S.lanes = lanes;

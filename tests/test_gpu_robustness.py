@@ -243,6 +243,25 @@ def test_thin_launch_is_bit_identical(oracle, systems, monkeypatch, lanes, nseg)
     eng.close()
 
 
+def test_launch_between_one_and_two_ctas_per_sm(oracle, systems, monkeypatch):
+    """20 000 systems need two CTAs on some SMs: the launch planner spreads them evenly over two CTAs on
+    every SM (17 lanes per warp). Same bits as the full-warp launch; a sample against the oracle."""
+    import nauyaca_b200 as nb
+    spec = systems["doc2"]; osys = oracle.OracleSystem(spec)
+    X = np.random.default_rng(33).random((20000, spec["ndim"]))
+    eng = nb.BatchEngine(spec)
+    chi2, logl, st = eng.loglike(X, mode=0)
+    eng.close()
+    monkeypatch.setenv("TTVB_LANES", "32")
+    eng = nb.BatchEngine(spec)
+    c32, l32, s32 = eng.loglike(X, mode=0)
+    eng.close()
+    _same(chi2, c32); _same(st, s32); _same(logl, l32)
+    idx = np.r_[0:150, 9900:10050, 19850:20000]
+    o = osys.loglike(X[idx], mode=0)
+    _same(chi2[idx], o[0]); _same(st[idx], o[2])
+
+
 def test_observed_table_variants(oracle):
     """Planets without observations, unsorted epoch order in the table, epochs the simulation
     never reaches (1e20 each, utils.py:199-206), barycentric-Julian-date sized times."""
