@@ -3,15 +3,17 @@
 # kernel ($1 = 2 or 3), the loop's span and its forward branches (scripts/sass_loops.py style).
 set -e -o pipefail
 N=${1:-2}
+ROOT=$(cd "$(dirname "$0")/.." && pwd)
+mkdir -p "$ROOT/build"
 cd /tmp
 rm -f /tmp/t23.so
-nvcc -gencode arch=compute_100a,code=sm_100a -O3 -fmad=false -std=c++17 -lineinfo -shared -Xcompiler -fPIC -DTTVB_DEV_ONLY_23 -Xptxas -v -o /tmp/t23.so /root/repo/nauyaca_b200/csrc/ttvb.cu 2>&1 | grep -B1 "spill" | grep -A1 "run_steps\|process_batch" | grep -v "^--" | paste - - | sed 's/ptxas info    : Function properties for //' | awk '{print $1, $2, $3, $4, $5, $6, $7, $8, $9, $10, $11, $12, $13, $14}'
-cuobjdump -sass /tmp/t23.so | awk -v n="$N" '/Function : /{f = ($0 ~ ("ttvb_main_kernelILi" n "ELb0"))} f' > /root/repo/build/k${N}b.sass
-python - "$N" <<'PY'
+nvcc -gencode arch=compute_100a,code=sm_100a -O3 -fmad=false -std=c++17 -lineinfo -shared -Xcompiler -fPIC -DTTVB_DEV_ONLY_23 -Xptxas -v -o /tmp/t23.so "$ROOT/nauyaca_b200/csrc/ttvb.cu" 2>&1 | grep -B1 "spill" | grep -A1 "run_steps\|process_batch" | grep -v "^--" | paste - - | sed 's/ptxas info    : Function properties for //' | awk '{print $1, $2, $3, $4, $5, $6, $7, $8, $9, $10, $11, $12, $13, $14}'
+cuobjdump -sass /tmp/t23.so | awk -v n="$N" '/Function : /{f = ($0 ~ ("ttvb_main_kernelILi" n "ELb0"))} f' > "$ROOT/build/k${N}b.sass"
+python - "$N" "$ROOT" <<'PY'
 import re, sys
-n = sys.argv[1]
+n, root = sys.argv[1], sys.argv[2]
 ins = []
-for line in open(f'/root/repo/build/k{n}b.sass'):
+for line in open(f'{root}/build/k{n}b.sass'):
     m = re.match(r'\s+/\*([0-9a-f]{4,})\*/\s+(.*?);', line)
     if m: ins.append((int(m.group(1), 16), m.group(2).strip()))
 def tgt(s):
