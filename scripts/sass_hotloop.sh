@@ -7,7 +7,7 @@ ROOT=$(cd "$(dirname "$0")/.." && pwd)
 mkdir -p "$ROOT/build"
 cd /tmp
 rm -f /tmp/t23.so
-nvcc -gencode arch=compute_100a,code=sm_100a -O3 -fmad=false -std=c++17 -lineinfo -shared -Xcompiler -fPIC -DTTVB_DEV_ONLY_23 -Xptxas -v -o /tmp/t23.so "$ROOT/nauyaca_b200/csrc/ttvb.cu" 2>&1 | grep -B1 "spill" | grep -A1 "run_steps\|process_batch" | grep -v "^--" | paste - - | sed 's/ptxas info    : Function properties for //' | awk '{print $1, $2, $3, $4, $5, $6, $7, $8, $9, $10, $11, $12, $13, $14}'
+nvcc -gencode arch=compute_100a,code=sm_100a -O3 -fmad=false -std=c++17 -lineinfo -shared -Xcompiler -fPIC -DTTVB_DEV_ONLY_23 ${TTVB_EXTRA} -Xptxas -v -o /tmp/t23.so "$ROOT/nauyaca_b200/csrc/ttvb.cu" 2>&1 | grep -B1 "spill" | grep -A1 "run_steps\|process_batch" | grep -v "^--" | paste - - | sed 's/ptxas info    : Function properties for //' | awk '{print $1, $2, $3, $4, $5, $6, $7, $8, $9, $10, $11, $12, $13, $14}'
 cuobjdump -sass /tmp/t23.so | awk -v n="$N" '/Function : /{f = ($0 ~ ("ttvb_main_kernelILi" n "ELb0"))} f' > "$ROOT/build/k${N}b.sass"
 python - "$N" "$ROOT" <<'PY'
 import re, sys
