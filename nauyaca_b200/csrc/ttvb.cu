@@ -400,10 +400,10 @@ int ttvb_create(const ttvb_system* sys, int device, ttvb_handle** out) {
     S.obs_epoch = h->d_obs_epoch; S.obs_time = h->d_obs_time; S.obs_sigma = h->d_obs_sigma;
 #ifndef TTVB_NO_CONST_COEF
     {
-        // Stumpff series coefficients of the constant-bank build (ttvb_math.cuh)
-        const double kc[14] = {1.0 / 2.0, -1.0 / 24.0, 1.0 / 720.0, -1.0 / 40320.0, 1.0 / 3628800.0, -1.0 / 479001600.0,
+        // the constant-bank literals of the hot loop (ttvb_math.cuh)
+        const double kc[16] = {1.0 / 2.0, -1.0 / 24.0, 1.0 / 720.0, -1.0 / 40320.0, 1.0 / 3628800.0, -1.0 / 479001600.0,
                                1.0 / 87178291200.0, 1.0 / 6.0, -1.0 / 120.0, 1.0 / 5040.0, -1.0 / 362880.0,
-                               1.0 / 39916800.0, -1.0 / 6227020800.0, 1.0 / 1307674368000.0};
+                               1.0 / 39916800.0, -1.0 / 6227020800.0, 1.0 / 1307674368000.0, 1.0 / 3.0, 0.0};
         if (cudaMemcpyToSymbol(ttvb::TTVB_STUMPFF_C, kc, sizeof(kc)) != cudaSuccess)
             return bail(fail(TTVB_E_CUDA, "upload of the series coefficients failed"));
     }
