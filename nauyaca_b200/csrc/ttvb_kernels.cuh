@@ -641,6 +641,7 @@ ttvb_main_kernel(const __grid_constant__ DevSys S) {
     const int rowlen = S.rowlen;
 
     __shared__ int s_unit;
+    __shared__ int s_rows_ok;      // streamed input: the rows of the tile have arrived (its own word: s_unit may still be being read)
     const int nunits = (int)ntiles * S.nseg;
     for (;;) {
         __syncthreads();   // previous unit done with shared memory; obs table visible
@@ -733,12 +734,12 @@ ttvb_main_kernel(const __grid_constant__ DevSys S) {
                             break;
                         }
                     }
-                    s_unit = ok ? unit : -1 - unit;
+                    s_rows_ok = ok;
                     __threadfence();     // acquire (the row counter was observed by this thread)
                 }
                 __syncthreads();
                 __threadfence();
-                arrived = s_unit >= 0;
+                arrived = s_rows_ok != 0;
                 if (!arrived) { status |= 32; alive = false; }
                 __syncthreads();
             }
