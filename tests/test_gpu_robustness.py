@@ -262,6 +262,32 @@ def test_launch_between_one_and_two_ctas_per_sm(oracle, systems, monkeypatch):
     _same(chi2[idx], o[0]); _same(st[idx], o[2])
 
 
+def test_repeated_launches_give_the_same_bits(systems, monkeypatch):
+    """A race (inter-CTA hand-over of time segments, event queues, staging / ring aliasing) would show up
+    as a result that changes from launch to launch: the same 40 000 systems twelve times, cut into three
+    time segments, through the device-pointer and the host-pointer path, must give ONE set of bits
+    (scripts/determinism_check.py does the same for the benchmark shapes)."""
+    import hashlib
+    import torch
+    import nauyaca_b200 as nb
+    spec = systems["sys3"]
+    monkeypatch.setenv("TTVB_NSEG", "3")
+    eng = nb.BatchEngine(spec)
+    X = np.random.default_rng(34).random((40000, spec["ndim"]))
+    Xd = torch.from_numpy(X).cuda()
+    seen = set()
+    for i in range(12):
+        if i % 3 == 2:
+            chi2, logl, st = eng.loglike(X, mode=0)
+        else:
+            c, l, s_ = eng.loglike(Xd, mode=0)
+            torch.cuda.synchronize()
+            chi2, st = c.cpu().numpy(), s_.cpu().numpy()
+        seen.add(hashlib.sha1(chi2.tobytes() + st.tobytes()).hexdigest())
+    assert len(seen) == 1
+    eng.close()
+
+
 def test_observed_table_variants(oracle):
     """Planets without observations, unsorted epoch order in the table, epochs the simulation
     never reaches (1e20 each, utils.py:199-206), barycentric-Julian-date sized times."""
